@@ -1,0 +1,350 @@
+// extern "C" entry points of libgml_b200 (declared in include/gml_b200.h): argument checking,
+// workspace carving, kernel-path selection.  No state, no allocation, nothing throws.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gml {
+
+static thread_local char g_last_cuda_error[256] = "";
+
+void set_last_cuda_error(cudaError_t e, const char* what) {
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s (%s)", what, cudaGetErrorName(e),
+           cudaGetErrorString(e));
+}
+
+namespace {
+
+struct Dims {
+  int n, c_v, c_s, hw_v, hw_s, d, ldz, zrows, hoff;
+};
+
+int check_dims(const gml_mmtm_dims* in, int mode, Dims* o) {
+  if (!in) return GML_E_BADARG;
+  if (mode < GML_MODE_NORMAL || mode > GML_MODE_XMODAL_OFF) return GML_E_BADARG;
+  if (in->n < 0 || in->c_v <= 0 || in->c_s <= 0 || in->hw_v <= 0 || in->hw_s <= 0 || in->d <= 0) return GML_E_BADARG;
+  if ((long long)in->n * in->c_v >= (1LL << 31) || (long long)in->n * in->c_s >= (1LL << 31)) return GML_E_UNSUPPORTED;
+  // the reference sizes BOTH running means by dim_visual and feeds both from the visual gate
+  // (balanced_mmtm.py:30-31,113-114); substituting the skeleton gate therefore needs c_s == c_v.
+  if (mode == GML_MODE_CURATE_SKELETON && in->c_s != in->c_v) return GML_E_UNSUPPORTED;
+  o->n = in->n; o->c_v = in->c_v; o->c_s = in->c_s; o->hw_v = in->hw_v; o->hw_s = in->hw_s; o->d = in->d;
+  o->ldz = in->c_v + in->c_s;
+  o->zrows = mode == GML_MODE_XMODAL_OFF ? 2 * in->n : in->n;
+  o->hoff = mode == GML_MODE_XMODAL_OFF ? in->n : 0;  // row offset of the hidden state that feeds g_b
+  return GML_OK;
+}
+
+// How many samples to push through both passes before moving on, so that the second pass
+// (gating / gradient apply) re-reads its input from L2 instead of HBM.  B200 has ~126 MB of L2;
+// the default budget leaves room for the output lines that are being written back.
+size_t l2_budget_bytes() {
+  static size_t v = [] {
+    const char* e = getenv("GML_L2_CHUNK_MB");
+    long mb = e ? atol(e) : 40;
+    if (mb < 1) mb = 1;
+    return (size_t)mb << 20;
+  }();
+  return v;
+}
+
+int chunk_samples(const Dims& d, size_t bytes_per_sample) {
+  size_t n = l2_budget_bytes() / (bytes_per_sample ? bytes_per_sample : 1);
+  if (n < 1) n = 1;
+  return n > (size_t)d.n ? d.n : (int)n;
+}
+
+bool live_a(int mode) { return mode != GML_MODE_CURATE_VISUAL; }
+bool live_b(int mode) { return mode != GML_MODE_CURATE_SKELETON; }
+
+// squeeze + excitation for samples [n0, n0 + cn)
+int gates_chunk(const float* a, const float* b, const float* w_sq, const float* b_sq, const float* w_v,
+                const float* b_v, const float* w_s, const float* b_s, float* z, float* h, float* g_a, float* g_b,
+                const float* m_a, const float* m_b, const Dims& d, int mode, int n0, int cn, bool keep, cudaStream_t st) {
+  const bool x3 = mode == GML_MODE_XMODAL_OFF;
+  float* z_a = z + (size_t)n0 * d.ldz;                               // rows that receive s_a
+  float* z_b = z + (size_t)(d.hoff + n0) * d.ldz;                    // rows that receive s_b
+  if (x3) {
+    GML_TRY(launch_fill_rows(z_a, cn, d.ldz, d.c_v, m_b, d.c_s, st));  // [s_a | m_b]
+    GML_TRY(launch_fill_rows(z_b, cn, d.ldz, 0, m_a, d.c_v, st));      // [m_a | s_b]
+  }
+  ReduceSeg sa{a + (size_t)n0 * d.c_v * d.hw_v, nullptr, z_a, nullptr, cn * d.c_v, d.hw_v, d.c_v, d.ldz, 0, 1.f};
+  ReduceSeg sb{b + (size_t)n0 * d.c_s * d.hw_s, nullptr, z_b, nullptr, cn * d.c_s, d.hw_s, d.c_s, d.ldz, d.c_v, 1.f};
+  GML_TRY(launch_plane_mean(sa, sb, keep, st));
+  // H = relu(Z Wsq^T + bsq)
+  GemmDesc g1[2];
+  int cnt1 = 1;
+  g1[0] = GemmDesc{z_a, w_sq, h + (size_t)n0 * d.d, b_sq, nullptr, cn, d.d, d.ldz, d.ldz, d.ldz, d.d, 0, 1, 1, kActRelu, 0};
+  if (x3) {
+    g1[1] = g1[0];
+    g1[1].a = z_b;
+    g1[1].c = h + (size_t)(d.hoff + n0) * d.d;
+    cnt1 = 2;
+  }
+  GML_TRY(launch_gemm(g1, cnt1, st));
+  // gates
+  GemmDesc g2[2];
+  g2[0] = GemmDesc{h + (size_t)n0 * d.d, w_v, g_a + (size_t)n0 * d.c_v, b_v, nullptr, cn, d.c_v, d.d, d.d, d.d, d.c_v, 0, 1, 1, kActSigmoid, 0};
+  g2[1] = GemmDesc{h + (size_t)(d.hoff + n0) * d.d, w_s, g_b + (size_t)n0 * d.c_s, b_s, nullptr, cn, d.c_s, d.d, d.d, d.d, d.c_s, 0, 1, 1, kActSigmoid, 0};
+  GML_TRY(launch_gemm(g2, 2, st));
+  return GML_OK;
+}
+
+int apply_chunk(const float* a, const float* b, float* a_out, float* b_out, const float* g_a, const float* g_b,
+                const float* run_v, const float* run_s, const Dims& d, int mode, float gate_scale, int n0, int cn,
+                bool do_a, bool do_b, cudaStream_t st) {
+  ScaleSeg sa{a + (size_t)n0 * d.c_v * d.hw_v, a_out + (size_t)n0 * d.c_v * d.hw_v,
+              live_a(mode) ? g_a + (size_t)n0 * d.c_v : run_v, nullptr, do_a ? cn * d.c_v : 0, d.hw_v, d.c_v,
+              live_a(mode) ? 0 : 1, 0, 0, gate_scale};
+  ScaleSeg sb{b + (size_t)n0 * d.c_s * d.hw_s, b_out + (size_t)n0 * d.c_s * d.hw_s,
+              live_b(mode) ? g_b + (size_t)n0 * d.c_s : run_s, nullptr, do_b ? cn * d.c_s : 0, d.hw_s, d.c_s,
+              live_b(mode) ? 0 : 1, 0, 0, gate_scale};
+  return launch_plane_scale(sa, sb, false, st);
+}
+
+}  // namespace
+}  // namespace gml
+
+using namespace gml;
+
+extern "C" int gml_abi_version(void) { return GML_ABI_VERSION; }
+
+extern "C" const char* gml_error_string(int code) {
+  switch (code) {
+    case GML_OK: return "ok";
+    case GML_E_BADARG: return "bad argument (null pointer, non-positive size or unknown mode)";
+    case GML_E_ALIGN: return "misaligned pointer";
+    case GML_E_WORKSPACE: return "workspace too small";
+    case GML_E_CUDA: return "CUDA runtime error (see gml_last_cuda_error)";
+    case GML_E_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error code";
+  }
+}
+
+extern "C" const char* gml_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" int gml_device_is_blackwell(void) {
+  int dev = 0, major = 0;
+  GML_CUDA_TRY(cudaGetDevice(&dev));
+  GML_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" size_t gml_mmtm_fwd_workspace_bytes(const gml_mmtm_dims* dims) {
+  (void)dims;
+  return 256;  // reserved (the current kernels keep everything in the caller-visible outputs)
+}
+
+extern "C" int gml_mmtm_gates(const float* a, const float* b, const float* w_sq, const float* b_sq, const float* w_v,
+                              const float* b_v, const float* w_s, const float* b_s, float* z, float* h, float* g_a,
+                              float* g_b, float* gate_sum, const float* m_a, const float* m_b, void* workspace,
+                              size_t workspace_bytes, const gml_mmtm_dims* dims, int mode, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  Dims d;
+  GML_TRY(check_dims(dims, mode, &d));
+  if (!a || !b || !w_sq || !b_sq || !w_v || !b_v || !w_s || !b_s || !z || !h || !g_a || !g_b) return GML_E_BADARG;
+  if (mode == GML_MODE_XMODAL_OFF && (!m_a || !m_b)) return GML_E_BADARG;
+  if (d.n == 0) return GML_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GML_TRY(gates_chunk(a, b, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, m_a, m_b, d, mode, 0, d.n, false, st));
+  if (gate_sum) GML_TRY(launch_colsum(g_a, d.n, d.c_v, d.c_v, gate_sum, st));
+  return GML_OK;
+}
+
+extern "C" int gml_mmtm_running(float* run_v, float* run_s, const float* gate_sum, int32_t c_v, int64_t n_total,
+                                int64_t step, void* stream) {
+  if (!run_v || !gate_sum || c_v <= 0 || n_total <= 0 || step < 0) return GML_E_BADARG;
+  return launch_running_update(run_v, run_s, gate_sum, c_v, (double)n_total, (double)step,
+                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gml_mmtm_apply(const float* a, const float* b, float* a_out, float* b_out, const float* g_a,
+                              const float* g_b, const float* run_v, const float* run_s, const gml_mmtm_dims* dims,
+                              int mode, float gate_scale, void* stream) {
+  Dims d;
+  GML_TRY(check_dims(dims, mode, &d));
+  if (!a || !b || !a_out || !b_out || !g_a || !g_b) return GML_E_BADARG;
+  if ((mode == GML_MODE_CURATE_VISUAL && !run_v) || (mode == GML_MODE_CURATE_SKELETON && !run_s)) return GML_E_BADARG;
+  if (d.n == 0) return GML_OK;
+  return apply_chunk(a, b, a_out, b_out, g_a, g_b, run_v, run_s, d, mode, gate_scale, 0, d.n, true, true,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float* b_out, const float* w_sq,
+                            const float* b_sq, const float* w_v, const float* b_v, const float* w_s, const float* b_s,
+                            float* z, float* h, float* g_a, float* g_b, float* gate_sum, float* run_v, float* run_s,
+                            int64_t step, const float* m_a, const float* m_b, void* workspace, size_t workspace_bytes,
+                            const gml_mmtm_dims* dims, int mode, float gate_scale, uint32_t flags, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  Dims d;
+  GML_TRY(check_dims(dims, mode, &d));
+  if (!a || !b || !a_out || !b_out || !w_sq || !b_sq || !w_v || !b_v || !w_s || !b_s || !z || !h || !g_a || !g_b ||
+      !gate_sum)
+    return GML_E_BADARG;
+  if (mode == GML_MODE_XMODAL_OFF && (!m_a || !m_b)) return GML_E_BADARG;
+  const bool update = !(flags & GML_F_NO_RUNNING_UPDATE);
+  if (update && (!run_v || !run_s || step < 0)) return GML_E_BADARG;
+  const bool curate = mode == GML_MODE_CURATE_VISUAL || mode == GML_MODE_CURATE_SKELETON;
+  if (curate && (!run_v || !run_s)) return GML_E_BADARG;
+  if (d.n == 0) return GML_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const bool can_fuse = !(flags & GML_F_FORCE_STREAMING) && !curate &&
+                        fused_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
+  if ((flags & GML_F_FORCE_FUSED) && !can_fuse) return GML_E_UNSUPPORTED;
+  if (can_fuse) {
+    FusedFwdArgs fa{a, b, a_out, b_out, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, run_v, run_s,
+                    d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
+    GML_TRY(launch_fused_fwd(fa, st));
+    GML_TRY(launch_colsum(g_a, d.n, d.c_v, d.c_v, gate_sum, st));
+    if (update) GML_TRY(launch_running_update(run_v, run_s, gate_sum, d.c_v, (double)d.n, (double)step, st));
+    return GML_OK;
+  }
+
+  // Streaming path: batch chunks sized for L2 so the gating pass re-reads from L2.
+  const size_t per_sample = ((size_t)d.c_v * d.hw_v + (size_t)d.c_s * d.hw_s) * sizeof(float);
+  const int cs = chunk_samples(d, per_sample);
+  const bool keep = true;
+  for (int n0 = 0; n0 < d.n; n0 += cs) {
+    const int cn = (d.n - n0) < cs ? (d.n - n0) : cs;
+    GML_TRY(gates_chunk(a, b, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, m_a, m_b, d, mode, n0, cn, keep, st));
+    // live sides can be gated right away; a substituted side waits for the running mean
+    GML_TRY(apply_chunk(a, b, a_out, b_out, g_a, g_b, run_v, run_s, d, mode, gate_scale, n0, cn, live_a(mode),
+                        live_b(mode), st));
+  }
+  GML_TRY(launch_colsum(g_a, d.n, d.c_v, d.c_v, gate_sum, st));
+  if (update) GML_TRY(launch_running_update(run_v, run_s, gate_sum, d.c_v, (double)d.n, (double)step, st));
+  if (curate) {
+    // balanced_mmtm.py:139-152: the substituted scale is the running mean INCLUDING this batch.
+    // With GML_F_NO_RUNNING_UPDATE the caller has already folded the (all-reduced) batch in.
+    GML_TRY(apply_chunk(a, b, a_out, b_out, g_a, g_b, run_v, run_s, d, mode, gate_scale, 0, d.n, !live_a(mode),
+                        !live_b(mode), st));
+  }
+  return GML_OK;
+}
+
+extern "C" size_t gml_mmtm_bwd_workspace_bytes(const gml_mmtm_dims* dims) {
+  if (!dims || dims->n < 0) return 0;
+  const size_t n = (size_t)dims->n, ldz = (size_t)dims->c_v + dims->c_s, dd = (size_t)dims->d;
+  // de_a [N,c_v] + de_b [N,c_s] + dh [2N,D] + dz [2N,ldz]   (2N rows cover mode 3)
+  return 256 + sizeof(float) * (n * ldz + 2 * n * dd + 2 * n * ldz) + 4 * 256;
+}
+
+extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a, const float* b, const float* w_sq,
+                            const float* w_v, const float* w_s, const float* z, const float* h, const float* g_a,
+                            const float* g_b, const float* run_v, const float* run_s, const float* m_a,
+                            const float* m_b, float* d_a, float* d_b, float* d_w_sq, float* d_b_sq, float* d_w_v,
+                            float* d_b_v, float* d_w_s, float* d_b_s, void* workspace, size_t workspace_bytes,
+                            const gml_mmtm_dims* dims, int mode, float gate_scale, uint32_t flags, void* stream) {
+  (void)m_a; (void)m_b;  // mode 3: the constant halves of Z are already stored in z
+  Dims d;
+  GML_TRY(check_dims(dims, mode, &d));
+  if (!go_a || !go_b || !a || !b || !w_sq || !w_v || !w_s || !z || !h || !g_a || !g_b || !d_a || !d_b || !workspace)
+    return GML_E_BADARG;
+  if ((mode == GML_MODE_CURATE_VISUAL && !run_v) || (mode == GML_MODE_CURATE_SKELETON && !run_s)) return GML_E_BADARG;
+  if (workspace_bytes < gml_mmtm_bwd_workspace_bytes(dims)) return GML_E_WORKSPACE;
+  if (d.n == 0) return GML_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool la = live_a(mode), lb = live_b(mode), x3 = mode == GML_MODE_XMODAL_OFF;
+
+  char* wp = static_cast<char*>(workspace);
+  auto carve = [&](size_t floats) {
+    float* p = reinterpret_cast<float*>(wp);
+    wp += round_up(floats * sizeof(float), 256);
+    return p;
+  };
+  float* de_a = carve((size_t)d.n * d.c_v);
+  float* de_b = carve((size_t)d.n * d.c_s);
+  float* dh = carve((size_t)2 * d.n * d.d);
+  float* dz = carve((size_t)2 * d.n * d.ldz);
+
+  const bool can_fuse = !(flags & GML_F_FORCE_STREAMING) && la && lb &&
+                        fused_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
+  if ((flags & GML_F_FORCE_FUSED) && !can_fuse) return GML_E_UNSUPPORTED;
+  if (can_fuse) {
+    FusedBwdArgs fb{go_a, go_b, a, b, w_sq, w_v, w_s, z, h, g_a, g_b, run_v, run_s, d_a, d_b, de_a, de_b, dh,
+                    d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
+    GML_TRY(launch_fused_bwd(fb, st));
+  } else {
+    // grad_out is read twice (dot, then apply): keep it in L2 per chunk.  a/b stream through once.
+    const size_t per_sample = ((size_t)d.c_v * d.hw_v + (size_t)d.c_s * d.hw_s) * sizeof(float);
+    const int cs = chunk_samples(d, per_sample);
+    for (int n0 = 0; n0 < d.n; n0 += cs) {
+      const int cn = (d.n - n0) < cs ? (d.n - n0) : cs;
+      const size_t oa = (size_t)n0 * d.c_v * d.hw_v, ob = (size_t)n0 * d.c_s * d.hw_s;
+      // 1. dE = gate_scale * <grad_out, input>_hw * g (1 - g) on live sides
+      ReduceSeg ra{go_a + oa, a + oa, de_a + (size_t)n0 * d.c_v, g_a + (size_t)n0 * d.c_v, la ? cn * d.c_v : 0,
+                   d.hw_v, d.c_v, d.c_v, 0, gate_scale};
+      ReduceSeg rb{go_b + ob, b + ob, de_b + (size_t)n0 * d.c_s, g_b + (size_t)n0 * d.c_s, lb ? cn * d.c_s : 0,
+                   d.hw_s, d.c_s, d.c_s, 0, gate_scale};
+      GML_TRY(launch_plane_dgate(ra, rb, true, st));
+      // 2. dH = (dE_a Wv + dE_b Ws) * [H > 0]
+      float* dh_a = dh + (size_t)n0 * d.d;
+      float* dh_b = dh + (size_t)(d.hoff + n0) * d.d;
+      const float* h_a = h + (size_t)n0 * d.d;
+      const float* h_b = h + (size_t)(d.hoff + n0) * d.d;
+      GemmDesc ga{de_a + (size_t)n0 * d.c_v, w_v, dh_a, nullptr, h_a, cn, d.d, d.c_v, d.c_v, d.d, d.d, d.d, 1, 0, kActNone, 0};
+      GemmDesc gb{de_b + (size_t)n0 * d.c_s, w_s, dh_b, nullptr, h_b, cn, d.d, d.c_s, d.c_s, d.d, d.d, d.d, 1, 0, kActReluMask, 0};
+      if (x3) {  // two independent hidden states
+        ga.act = kActReluMask;
+        GemmDesc both[2] = {ga, gb};
+        GML_TRY(launch_gemm(both, 2, st));
+      } else if (la && lb) {
+        GML_TRY(launch_gemm(&ga, 1, st));
+        gb.beta = 1;
+        GML_TRY(launch_gemm(&gb, 1, st));
+      } else if (la) {
+        ga.act = kActReluMask;
+        GML_TRY(launch_gemm(&ga, 1, st));
+      } else {
+        GML_TRY(launch_gemm(&gb, 1, st));
+      }
+      // 3. dZ = dH Wsq
+      GemmDesc gz[2];
+      gz[0] = GemmDesc{dh_a, w_sq, dz + (size_t)n0 * d.ldz, nullptr, nullptr, cn, d.ldz, d.d, d.d, d.ldz, d.ldz, 0, 1, 0, kActNone, 0};
+      int cz = 1;
+      if (x3) {
+        gz[1] = gz[0];
+        gz[1].a = dh_b;
+        gz[1].c = dz + (size_t)(d.hoff + n0) * d.ldz;
+        cz = 2;
+      }
+      GML_TRY(launch_gemm(gz, cz, st));
+      // 4. d_input = grad_out * scale + ds / HW
+      ScaleSeg sa{go_a + oa, d_a + oa, la ? g_a + (size_t)n0 * d.c_v : run_v, dz + (size_t)n0 * d.ldz, cn * d.c_v,
+                  d.hw_v, d.c_v, la ? 0 : 1, d.ldz, 0, gate_scale};
+      ScaleSeg sb{go_b + ob, d_b + ob, lb ? g_b + (size_t)n0 * d.c_s : run_s, dz + (size_t)(d.hoff + n0) * d.ldz,
+                  cn * d.c_s, d.hw_s, d.c_s, lb ? 0 : 1, d.ldz, d.c_v, gate_scale};
+      GML_TRY(launch_plane_scale(sa, sb, true, st));
+    }
+  }
+
+  // 5. weight gradients over the whole batch (reduction over samples inside one CTA per tile:
+  //    deterministic, no atomics)
+  GemmDesc gw[2];
+  int cw = 0;
+  if (d_w_v) {
+    if (la) gw[cw++] = GemmDesc{de_a, h, d_w_v, nullptr, nullptr, d.c_v, d.d, d.n, d.c_v, d.d, d.d, 0, 0, 0, kActNone, 0};
+    else GML_TRY(launch_fill_zero(d_w_v, (size_t)d.c_v * d.d, st));
+  }
+  if (d_w_s) {
+    if (lb) gw[cw++] = GemmDesc{de_b, h + (size_t)d.hoff * d.d, d_w_s, nullptr, nullptr, d.c_s, d.d, d.n, d.c_s, d.d, d.d, 0, 0, 0, kActNone, 0};
+    else GML_TRY(launch_fill_zero(d_w_s, (size_t)d.c_s * d.d, st));
+  }
+  if (cw) GML_TRY(launch_gemm(gw, cw, st));
+  if (d_w_sq) {
+    GemmDesc gq{dh, z, d_w_sq, nullptr, nullptr, d.d, d.ldz, d.zrows, d.d, d.ldz, d.ldz, 0, 0, 0, kActNone, 0};
+    GML_TRY(launch_gemm(&gq, 1, st));
+  }
+  if (d_b_v) {
+    if (la) GML_TRY(launch_colsum(de_a, d.n, d.c_v, d.c_v, d_b_v, st));
+    else GML_TRY(launch_fill_zero(d_b_v, d.c_v, st));
+  }
+  if (d_b_s) {
+    if (lb) GML_TRY(launch_colsum(de_b, d.n, d.c_s, d.c_s, d_b_s, st));
+    else GML_TRY(launch_fill_zero(d_b_s, d.c_s, st));
+  }
+  if (d_b_sq) GML_TRY(launch_colsum(dh, d.zrows, d.d, d.d, d_b_sq, st));
+  return GML_OK;
+}

@@ -1,0 +1,99 @@
+// Internal launch interfaces between the translation units of libgml_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gml {
+
+// ---- streaming plane kernels (stream_kernels.cu) -----------------------------------------
+constexpr int kEpiMean = 0;   // out = sum / HW
+constexpr int kEpiDGate = 1;  // out = mul * sum * g * (1 - g)
+
+struct ReduceSeg {
+  const float* x;     // [rows, hw]
+  const float* y;     // [rows, hw] second operand of the dot (backward) or nullptr
+  float* out;         // out[n * out_ld + out_off + c]
+  const float* gate;  // [rows] (kEpiDGate)
+  int rows, hw, c;    // rows = N * c
+  int out_ld, out_off;
+  float mul;
+};
+struct ReduceLaunch {
+  ReduceSeg seg[2];
+  int seg_blocks0;
+  int keep_in_l2;
+};
+
+struct ScaleSeg {
+  const float* x;      // [rows, hw]
+  float* out;          // [rows, hw]
+  const float* scale;  // [rows] or [c] when scale_bcast
+  const float* add;    // add[n * add_ld + add_off + c], divided by hw (or nullptr)
+  int rows, hw, c;
+  int scale_bcast;
+  int add_ld, add_off;
+  float mul;
+};
+struct ScaleLaunch {
+  ScaleSeg seg[2];
+  int seg_blocks0;
+};
+
+int launch_plane_mean(const ReduceSeg& a, const ReduceSeg& b, bool keep_in_l2, cudaStream_t st);
+int launch_plane_dgate(const ReduceSeg& a, const ReduceSeg& b, bool keep_in_l2, cudaStream_t st);
+int launch_plane_scale(const ScaleSeg& a, const ScaleSeg& b, bool has_add, cudaStream_t st);
+
+// ---- small dense kernels (fc_kernels.cu) ---------------------------------------------------
+constexpr int kActNone = 0;
+constexpr int kActRelu = 1;      // C = max(acc + bias, 0)
+constexpr int kActSigmoid = 2;   // C = sigmoid(acc + bias)
+constexpr int kActReluMask = 3;  // C = (beta*C + acc) * [mask > 0]
+
+// C[M,N] (ldc) = beta * C + sum_k A(m,k) * B(k,n), fp32 on CUDA cores.
+//   a_kc: A(m,k) = a[m*lda + k]  else a[k*lda + m]
+//   b_kc: B(k,n) = b[n*ldb + k]  else b[k*ldb + n]
+struct GemmDesc {
+  const float* a; const float* b; float* c;
+  const float* bias;  // [N] or nullptr
+  const float* mask;  // [M, ldmask] for kActReluMask
+  int m, n, k;
+  int lda, ldb, ldc, ldmask;
+  int a_kc, b_kc;
+  int act;
+  int beta;           // 0 or 1
+};
+// up to two independent problems in one launch (blockIdx.z)
+int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st);
+
+// out[j] = sum_i x[i*ld + j], i < rows, j < cols  (fixed order)
+int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st);
+// z rows for mode 3: z[n, off + j] = v[j]
+int launch_fill_rows(float* z, int rows, int ld, int off, const float* v, int cols, cudaStream_t st);
+int launch_running_update(float* run_v, float* run_s, const float* gate_sum, int c, double n_total, double step,
+                          cudaStream_t st);
+int launch_fill_zero(float* p, size_t n, cudaStream_t st);
+
+// ---- fused cluster kernels (fused_kernels.cu) ------------------------------------------------
+struct FusedFwdArgs {
+  const float* a; const float* b; float* a_out; float* b_out;
+  const float* w_sq; const float* b_sq; const float* w_v; const float* b_v; const float* w_s; const float* b_s;
+  float* z; float* h; float* g_a; float* g_b;
+  const float* run_v; const float* run_s;
+  int n, c, hw, d, mode;
+  float gate_scale;
+};
+struct FusedBwdArgs {
+  const float* go_a; const float* go_b; const float* a; const float* b;
+  const float* w_sq; const float* w_v; const float* w_s;
+  const float* z; const float* h; const float* g_a; const float* g_b;
+  const float* run_v; const float* run_s;
+  float* d_a; float* d_b;
+  float* de_a; float* de_b; float* dh;  // [N,c],[N,c],[N,d] for the weight-gradient GEMMs
+  int n, c, hw, d, mode;
+  float gate_scale;
+};
+bool fused_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mode);
+int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st);
+int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st);
+
+}  // namespace gml
