@@ -1,0 +1,443 @@
+#!/usr/bin/env python3
+"""Benchmark of the MMTM hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one forward+backward of the three MMTM blocks of the 2-view ResNet-18
+(128x28^2, 256x14^2, 512x7^2) at batch 256 per GPU, fp32 -- the MMTM work of one
+`training_guided.gin` step at batch 256 (BASELINE.json configs[1] at the batch of configs[2]).
+Prints ONE JSON line (rank 0):
+
+  value      algorithmic GB/s (40*N*C*HW bytes per block) over all ranks, inputs
+             resident in HBM, the C-ABI calls of one step replayed from a CUDA graph
+  e2e        the same metric through the public Python API (MMTM_mitigate modules) with the
+             feature maps coming from PINNED HOST memory every step and the gates read back
+  roofline   dominant kernel class: algorithmic bytes / CUDA-event time per launch vs the
+             measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle port (torch CPU fp32, autograd backward = the reference's arithmetic)
+             on a bounded sample (batch 32), all host threads
+  train      guided 2-view training step end to end (cuDNN backbone + CUDA MMTM + one-launch
+             learning-speed statistic), samples/s, next to the CPU reference-path step
+
+`--impl reference` times only the CPU reference path (oracle port) on the same metric/config.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPES = ((128, 28), (256, 14), (512, 7))  # (C, H) of mmtm2/3/4 (src/model.py:58-60)
+METRIC = "mmtm_fwd_bwd_algorithmic_hbm_throughput"
+UNIT = "GB/s"
+
+
+def block_bytes(n, c, h):
+    """Algorithmic bytes of one block fwd+bwd: 10 u, u = N*C*HW*4."""
+    return 40 * n * c * h * h
+
+
+def step_bytes(n):
+    return sum(block_bytes(n, c, h) for c, h in SHAPES)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+class BlockBuffers:
+    """Device-resident buffers of one MMTM block for direct C-ABI calls."""
+
+    def __init__(self, torch, lib_mod, n, c, h, dev, seed):
+        from oracle import mmtm_oracle as mo
+        self.n, self.c, self.h, self.d = n, c, h, c
+        g = torch.Generator(device=dev).manual_seed(seed)
+        r = lambda *s: torch.randn(*s, device=dev, generator=g)
+        self.a, self.b, self.go_a, self.go_b = r(n, c, h, h), r(n, c, h, h), r(n, c, h, h), r(n, c, h, h)
+        self.a_out, self.b_out = torch.empty_like(self.a), torch.empty_like(self.b)
+        self.d_a, self.d_b = torch.empty_like(self.a), torch.empty_like(self.b)
+        p = mo.synth_params(seed, c, c)
+        self.w = [t.to(dev) for t in p.tensors()]  # w_sq, b_sq, w_v, b_v, w_s, b_s
+        self.dw = [torch.empty_like(t) for t in self.w]
+        f = lambda *s: torch.empty(*s, device=dev)
+        self.z, self.hid, self.g_a, self.g_b = f(n, 2 * c), f(n, c), f(n, c), f(n, c)
+        self.gate_sum, self.run_v, self.run_s = f(c), torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+        self.dims = lib_mod.MMTMDims(n, c, c, h * h, h * h, c)
+        lib = lib_mod.load()
+        self.ws_bytes = lib.gml_mmtm_bwd_workspace_bytes(self.dims)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+
+    def fwd_bwd(self, lib, lib_mod, stream, flags=0):
+        P = lambda t: t.data_ptr()
+        w = self.w
+        lib_mod.check(lib.gml_mmtm_fwd(P(self.a), P(self.b), P(self.a_out), P(self.b_out), P(w[0]), P(w[1]), P(w[2]),
+                                       P(w[3]), P(w[4]), P(w[5]), P(self.z), P(self.hid), P(self.g_a), P(self.g_b),
+                                       P(self.gate_sum), P(self.run_v), P(self.run_s), 0, None, None, None, 0,
+                                       self.dims, 0, 1.0, flags, stream), "gml_mmtm_fwd")
+        dw = self.dw
+        lib_mod.check(lib.gml_mmtm_bwd(P(self.go_a), P(self.go_b), P(self.a), P(self.b), P(w[0]), P(w[2]), P(w[4]),
+                                       P(self.z), P(self.hid), P(self.g_a), P(self.g_b), None, None, None, None,
+                                       P(self.d_a), P(self.d_b), P(dw[0]), P(dw[1]), P(dw[2]), P(dw[3]), P(dw[4]),
+                                       P(dw[5]), P(self.ws), self.ws_bytes, self.dims, 0, 1.0, flags, stream),
+                      "gml_mmtm_bwd")
+
+
+def time_events(torch, fn, steps, warmup, sync_ranks):
+    """W untimed + exactly K timed calls of fn between CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    sync_ranks()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    sync_ranks()
+    return e0.elapsed_time(e1) / steps  # ms per step
+
+
+def cpu_baseline_mmtm(torch, n=32, min_seconds=4.0, max_iters=40):
+    """Oracle port on the host cores: fwd+bwd of the three blocks at batch n (bounded sample)."""
+    from oracle import mmtm_oracle as mo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    work = []
+    for c, h in SHAPES:
+        x = mo.synth_inputs(c, n, c, h)
+        work.append((x, mo.synth_params(c, c, c), mo.MMTMState.zeros(c)))
+
+    def once():
+        for x, p, st in work:
+            mo.forward_backward(x["A"], x["B"], p, st, x["gA"], x["gB"])
+
+    once()
+    times, t_start = [], time.perf_counter()
+    while len(times) < max_iters and (len(times) < 5 or time.perf_counter() - t_start < min_seconds):
+        t0 = time.perf_counter()
+        once()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": step_bytes(n) / med / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle/mmtm_oracle.forward_backward (torch CPU fp32, autograd), 3 blocks at batch %d, "
+                      "median of %d iterations, %.1f ms each" % (n, len(times), med * 1e3),
+            "ms_per_step": med * 1e3, "batch": n}
+
+
+def cpu_baseline_train(torch, batch=8, iters=3):
+    """Reference-path training step on CPU: mirror model with the ORACLE MMTM + oracle statistic."""
+    import greedy_multimodal_learning_b200 as pkg
+    from oracle.mmtm_module import OracleMMTM
+    from oracle import stats_oracle as so
+    torch.manual_seed(777)
+    model = pkg.MMTM_MVCNN(mmtm_cls=OracleMMTM)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    x = torch.randn(batch, 2, 3, 224, 224)
+    y = torch.randint(0, 40, (batch,))
+    times = []
+    for i in range(iters + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        fused, views, _, _ = model(x)
+        loss = so.blend_loss(views, y)
+        loss.backward()
+        so.sqnorm_buckets(((n, p, p.grad) for n, p in model.named_parameters()), ["net_view_0", "net_view_1"],
+                          ["visual", "skeleton"])
+        opt.step()
+        for t in [fused] + views:
+            float(so.acc(t, y))
+        float(loss)
+        if i:
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"samples_per_s": batch / med, "batch": batch, "ms_per_step": med * 1e3, "cores": os.cpu_count(),
+            "kind": "port", "sample": "oracle-backed MMTM_MVCNN train step (fwd+loss+bwd+learning-speed+SGD), "
+                                      "batch %d, 224x224, median of %d" % (batch, iters)}
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_baseline_mmtm(torch, n=32, min_seconds=max(2.0, 0.3 * args.steps), max_iters=max(5, args.steps))
+    out = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "MMTM fwd+bwd, blocks 128x28^2+256x14^2+512x7^2, CPU reference path (oracle port), "
+                                  "bounded sample batch 32 of the batch-256 workload"},
+           "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import greedy_multimodal_learning_b200 as pkg
+    from greedy_multimodal_learning_b200 import _lib as L, dist as gdist
+    from oracle import mmtm_oracle as mo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        gdist.init_from_env("nccl")
+    lib = L.load()
+    if lib.gml_device_is_blackwell() != 1:
+        print("warning: not a compute-capability-10 device", file=sys.stderr)
+
+    def sync_ranks():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.batch
+    blocks = [BlockBuffers(torch, L, n, c, h, dev, seed=c + rank) for c, h in SHAPES]
+    stream = torch.cuda.Stream()
+    flags = {"auto": 0, "streaming": L.F_FORCE_STREAMING, "fused": L.F_FORCE_FUSED}[args.path]
+
+    def eager_step():
+        for b in blocks:
+            b.fwd_bwd(lib, L, stream.cuda_stream, flags)
+
+    # ---- value: C-ABI step replayed from a CUDA graph, inputs resident in HBM -------------------
+    with torch.cuda.stream(stream):
+        launches_before = lib.gml_launch_count(-1)
+        eager_step()
+        launches_per_step = lib.gml_launch_count(-1) - launches_before
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            eager_step()
+        with ClockSampler(local) as clk:
+            ms = time_events(torch, graph.replay, args.steps, args.warmup, sync_ranks)
+            # keep the GPU busy a little longer so the sampler sees clocks under load
+            t_end = time.time() + 0.6
+            while time.time() < t_end:
+                graph.replay()
+            torch.cuda.synchronize()
+    ms = max_over_ranks(ms)
+    total_bytes = step_bytes(n) * world
+    value = total_bytes / (ms * 1e-3) / 1e9
+    clocks = clk.summary()
+
+    # ---- roofline: per-kernel-class CUDA-event times over the same step (eager, profiled) ------
+    with torch.cuda.stream(stream):
+        lib.gml_profile_reset()
+        lib.gml_profile_enable(1)
+        for _ in range(max(3, min(args.steps, 10))):
+            eager_step()
+        stream.synchronize()
+        lib.gml_profile_enable(0)
+    prof_steps = max(3, min(args.steps, 10))
+    u_total = sum(n * c * h * h * 4 for c, h in SHAPES)  # one modality, all three blocks
+    alg_units = {"plane_mean": 2, "plane_scale_fwd": 4, "plane_dgate": 4, "plane_scale_bwd": 4, "fused_fwd": 4,
+                 "fused_bwd": 6}
+    kernels, dominant = {}, None
+    for tag in range(lib.gml_kernel_tag_count()):
+        tot, cnt = ctypes.c_double(), ctypes.c_int64()
+        lib.gml_profile_read(tag, ctypes.byref(tot), ctypes.byref(cnt))
+        name = lib.gml_kernel_tag_name(tag).decode()
+        if cnt.value:
+            per_step_ms = tot.value / prof_steps
+            entry = {"launches_per_step": cnt.value / prof_steps, "ms_per_step": per_step_ms}
+            if name in alg_units:
+                entry["algorithmic_gbs"] = alg_units[name] * u_total / (per_step_ms * 1e-3) / 1e9
+            kernels[name] = entry
+            if name in alg_units and (dominant is None or per_step_ms > kernels[dominant]["ms_per_step"]):
+                dominant = name
+    peak, peak_src = measured_peak()
+    roof = None
+    if dominant:
+        k = kernels[dominant]
+        roof = {"bound": "hbm", "kernel": dominant, "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": k["algorithmic_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": k["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
+                "whole_step_frac": value / world / peak}
+
+    # ---- e2e: public Python API, feature maps from pinned host memory, gates read back ----------
+    mods = []
+    for b in blocks:
+        m = pkg.MMTM_mitigate(b.c, b.c, 4, kernel_flags=flags)
+        with torch.no_grad():
+            for dst, src in zip((m.fc_squeeze.weight, m.fc_squeeze.bias, m.fc_visual.weight, m.fc_visual.bias,
+                                 m.fc_skeleton.weight, m.fc_skeleton.bias), b.w):
+                dst.copy_(src)
+        mods.append(m.to(dev))
+    host = [(b.a.cpu().pin_memory(), b.b.cpu().pin_memory()) for b in blocks]
+    h2d = sum(a.numel() * 4 + bb.numel() * 4 for a, bb in host)
+    d2h = sum(2 * b.n * b.c * 4 for b in blocks)
+
+    def e2e_step():
+        for m, b, (ha, hb) in zip(mods, blocks, host):
+            a = ha.to(dev, non_blocking=True).requires_grad_(True)
+            bb = hb.to(dev, non_blocking=True).requires_grad_(True)
+            a_out, b_out, scales, _ = m(a, bb, True)          # return_scale=True: gates come back to the host
+            torch.autograd.backward([a_out, b_out], [b.go_a, b.go_b])
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = max_over_ranks(time_events(torch, e2e_step, e2e_steps, min(args.warmup, 3), sync_ranks))
+    e2e = {"value": total_bytes / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps,
+           "api": "MMTM_mitigate.forward(return_scale=True) + autograd.backward, inputs from pinned host memory"}
+
+    # ---- train: guided 2-view training step end to end ----------------------------------------------
+    train = None
+    if not args.no_train:
+        train = bench_train(torch, pkg, gdist, dev, world, rank, args, sync_ranks, max_over_ranks)
+
+    out = None
+    if rank == 0:
+        cpu = cpu_baseline_mmtm(torch)
+        if train is not None and not args.no_cpu_train:
+            train["cpu_reference"] = cpu_baseline_train(torch)
+            train["speedup_vs_cpu_reference"] = train["samples_per_s"] / train["cpu_reference"]["samples_per_s"]
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "MMTM fwd+bwd, blocks 128x28^2+256x14^2+512x7^2 (mmtm2/3/4 of 2-view ResNet-18), "
+                                      "batch %d per GPU, normal mode" % n,
+                          "batch_per_gpu": n, "algorithmic_bytes_per_step_per_gpu": step_bytes(n),
+                          "cache": "per-step working set 8u = %.2f GB per GPU > 126 MB L2 (no flush needed)"
+                                   % (8 * u_total / 1e9),
+                          "kernel_path": args.path, "launch": "CUDA graph replay of the C-ABI calls"},
+               "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "launches_per_step":
+               int(launches_per_step), "e2e": e2e, "roofline": roof, "kernels": kernels,
+               "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+               "frac_of_measured_hbm_peak": value / world / peak, "train": train}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_train(torch, pkg, gdist, dev, world, rank, args, sync_ranks, max_over_ranks):
+    """training_guided.gin step: batch `--train-batch` per GPU, data parallel when world > 1."""
+    bsz = args.train_batch
+    gdist.seed_everything(777)
+    model = pkg.MMTM_MVCNN().to(dev)
+    if world > 1:
+        model, opt, reducer = gdist.setup_model(model, lambda p: torch.optim.SGD(p, lr=0.1, momentum=0, weight_decay=0))
+    else:
+        opt, reducer = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0, weight_decay=0), None
+    cb = pkg.Bias_Mitigation_Strong(0.01, 5, ["net_view_0", "net_view_1"], 1)
+    cb.set_model(model, ignore=False)
+    engine = pkg.Model_(model, opt, pkg.blend_loss, 2, metrics=[pkg.acc], data_parallel=reducer).to(dev)
+    cbs = pkg.CallbackList([cb])
+    cbs.set_model_pytoune(engine)
+    cbs.on_train_begin({})
+    cbs.on_epoch_begin(1, {})
+    g = torch.Generator().manual_seed(rank)
+    x = torch.randn(bsz, 2, 3, 224, 224, generator=g).pin_memory()
+    y = torch.randint(0, 40, (bsz,), generator=g).pin_memory()
+    model.train(True)
+    state = {"i": 0}
+
+    def step():
+        state["i"] += 1
+        s = {"number": state["i"], "indices": None}
+        engine.train_step(s, x, y, cbs)   # H2D of the batch + loss/accuracy read-back inside
+
+    steps = max(3, min(args.steps, 8))
+    ms = max_over_ranks(time_events(torch, step, steps, 3, sync_ranks))
+    sps = bsz * world / (ms * 1e-3)
+    peak, _ = measured_peak()
+    roofline_sps = peak * 1e9 / 7_024_640 * world
+    return {"samples_per_s": sps, "ms_per_step": ms, "global_batch": bsz * world, "steps": steps,
+            "config": "training_guided.gin: 2-view ResNet-18 + MMTM, 224x224, SGD lr 0.1, Bias_Mitigation_Strong "
+                      "eps 0.01 window 5, fp32 (cuDNN TF32 default on), H2D of the batch and loss/acc read-back timed",
+            "frac_of_mmtm_memory_roofline": sps / roofline_sps,
+            "curation_mode_at_end": bool(engine.curation_mode)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="MMTM batch per GPU")
+    ap.add_argument("--train-batch", type=int, default=256, help="training batch per GPU")
+    ap.add_argument("--path", default="auto", choices=["auto", "streaming", "fused"])
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu-train", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -13,6 +17,54 @@ static thread_local char g_last_cuda_error[256] = "";
 void set_last_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s (%s)", what, cudaGetErrorName(e),
            cudaGetErrorString(e));
+}
+
+// ---- launch accounting -------------------------------------------------------------------
+struct ProfRecord {
+  int tag;
+  cudaEvent_t start, stop;
+};
+static std::mutex g_prof_mu;
+static std::atomic<long long> g_launches[kTagCount];
+static std::atomic<int> g_prof_on{0};
+static std::vector<ProfRecord*> g_prof_pending;
+static double g_prof_ms[kTagCount];
+static long long g_prof_n[kTagCount];
+
+LaunchScope::LaunchScope(int tag, cudaStream_t st) : tag_(tag), st_(st), rec_(nullptr) {
+  g_launches[tag].fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on.load(std::memory_order_relaxed)) {
+    ProfRecord* r = new ProfRecord;
+    r->tag = tag;
+    if (cudaEventCreate(&r->start) != cudaSuccess || cudaEventCreate(&r->stop) != cudaSuccess) {
+      delete r;
+      return;
+    }
+    cudaEventRecord(r->start, st);
+    rec_ = r;
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (!rec_) return;
+  ProfRecord* r = static_cast<ProfRecord*>(rec_);
+  cudaEventRecord(r->stop, st_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_pending.push_back(r);
+}
+
+static void prof_drain() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (ProfRecord* r : g_prof_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r->stop) == cudaSuccess && cudaEventElapsedTime(&ms, r->start, r->stop) == cudaSuccess) {
+      g_prof_ms[r->tag] += ms;
+      g_prof_n[r->tag] += 1;
+    }
+    cudaEventDestroy(r->start);
+    cudaEventDestroy(r->stop);
+    delete r;
+  }
+  g_prof_pending.clear();
 }
 
 namespace {
@@ -123,6 +175,41 @@ extern "C" const char* gml_error_string(int code) {
 }
 
 extern "C" const char* gml_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" int64_t gml_launch_count(int tag) {
+  if (tag >= 0 && tag < kTagCount) return g_launches[tag].load();
+  long long t = 0;
+  for (int i = 0; i < kTagCount; ++i) t += g_launches[i].load();
+  return t;
+}
+
+extern "C" const char* gml_kernel_tag_name(int tag) {
+  static const char* names[kTagCount] = {"plane_mean", "plane_dgate", "plane_scale_fwd", "plane_scale_bwd",
+                                         "fc_gemm", "small", "fused_fwd", "fused_bwd", "sqnorm", "stats"};
+  return (tag >= 0 && tag < kTagCount) ? names[tag] : "";
+}
+
+extern "C" int gml_kernel_tag_count(void) { return kTagCount; }
+
+extern "C" void gml_profile_enable(int on) {
+  if (!on) prof_drain();
+  g_prof_on.store(on ? 1 : 0);
+}
+
+extern "C" void gml_profile_reset(void) {
+  prof_drain();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < kTagCount; ++i) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
+}
+
+extern "C" int gml_profile_read(int tag, double* total_ms, int64_t* launches) {
+  if (tag < 0 || tag >= kTagCount || !total_ms || !launches) return GML_E_BADARG;
+  prof_drain();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  *total_ms = g_prof_ms[tag];
+  *launches = g_prof_n[tag];
+  return GML_OK;
+}
 
 extern "C" int gml_device_is_blackwell(void) {
   int dev = 0, major = 0;

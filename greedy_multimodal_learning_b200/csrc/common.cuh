@@ -24,6 +24,29 @@ void set_last_cuda_error(cudaError_t e, const char* what);
 
 #define GML_LAUNCH_CHECK() GML_CUDA_TRY(cudaGetLastError())
 
+// ---- launch accounting / optional per-kernel timing (capi.cu) ----------------------------
+enum KernelTag {
+  kTagMean = 0,   // plane means (forward pass 1)
+  kTagDGate,      // <grad_out, input> plane dots (backward pass 1)
+  kTagScaleFwd,   // gating pass
+  kTagScaleBwd,   // gradient apply pass
+  kTagGemm,       // squeeze/excitation FCs and their gradients
+  kTagSmall,      // column sums, fills, running-mean update
+  kTagFusedFwd,   // cluster/shared-memory-resident forward
+  kTagFusedBwd,   // cluster/shared-memory-resident backward
+  kTagSqnorm,     // multi-tensor sum of squares
+  kTagStats,      // squeeze accumulation, accuracy counts
+  kTagCount
+};
+// RAII around one kernel launch: counts it, and when profiling is on brackets it with events.
+struct LaunchScope {
+  LaunchScope(int tag, cudaStream_t st);
+  ~LaunchScope();
+  int tag_;
+  cudaStream_t st_;
+  void* rec_;
+};
+
 #define GML_TRY(expr)          \
   do {                         \
     int _r = (expr);           \

@@ -76,7 +76,7 @@ struct TileLoader {
 template <int BM, int BN>
 __global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_kernel(GemmBatch batch) {
   constexpr int T = (BM / 4) * (BN / 4);
-  const GemmDesc& d = batch.d[blockIdx.z];
+  const GemmDesc d = blockIdx.z ? batch.d[1] : batch.d[0];  // field-wise select, no local copy
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (m0 >= d.m || n0 >= d.n) return;
   __shared__ __align__(16) float As[2][BK][BM + 4];
@@ -200,9 +200,11 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st) {
   const long tiles64 = (long)ceil_div(max_m, 64) * ceil_div(max_n, 64) * count;
   if (tiles64 >= 120) {
     dim3 grid(ceil_div(max_n, 64), ceil_div(max_m, 64), count);
+    LaunchScope ls(kTagGemm, st);
     gemm_kernel<64, 64><<<grid, 256, 0, st>>>(batch);
   } else {
     dim3 grid(ceil_div(max_n, 32), ceil_div(max_m, 32), count);
+    LaunchScope ls(kTagGemm, st);
     gemm_kernel<32, 32><<<grid, 64, 0, st>>>(batch);
   }
   GML_LAUNCH_CHECK();
@@ -210,22 +212,25 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st) {
 }
 
 int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st) {
-  colsum_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(x, rows, cols, ld, out);
+  { LaunchScope ls(kTagSmall, st);
+  colsum_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(x, rows, cols, ld, out); }
   GML_LAUNCH_CHECK();
   return GML_OK;
 }
 
 int launch_fill_rows(float* z, int rows, int ld, int off, const float* v, int cols, cudaStream_t st) {
   const int total = rows * cols;
+  { LaunchScope ls(kTagSmall, st);
   fill_rows_kernel<<<ceil_div(total, 256) < 1024 ? ceil_div(total, 256) : 1024, 256, 0, st>>>(z, rows, ld, off, v,
-                                                                                            cols);
+                                                                                            cols); }
   GML_LAUNCH_CHECK();
   return GML_OK;
 }
 
 int launch_running_update(float* run_v, float* run_s, const float* gate_sum, int c, double n_total, double step,
                           cudaStream_t st) {
-  running_update_kernel<<<ceil_div(c, 128), 128, 0, st>>>(run_v, run_s, gate_sum, c, (float)n_total, (float)step);
+  { LaunchScope ls(kTagSmall, st);
+  running_update_kernel<<<ceil_div(c, 128), 128, 0, st>>>(run_v, run_s, gate_sum, c, (float)n_total, (float)step); }
   GML_LAUNCH_CHECK();
   return GML_OK;
 }
@@ -234,7 +239,8 @@ int launch_fill_zero(float* p, size_t n, cudaStream_t st) {
   if (n == 0) return GML_OK;
   size_t blocks = (n + 255) / 256;
   if (blocks > 1184) blocks = 1184;
-  fill_zero_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n);
+  { LaunchScope ls(kTagSmall, st);
+  fill_zero_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n); }
   GML_LAUNCH_CHECK();
   return GML_OK;
 }

@@ -203,6 +203,7 @@ extern "C" int gml_multi_tensor_sqnorm(const void* const* tensors_host, const in
     tab.n_tensors = cnt;
     int grid = kNumSMs * 8;
     if (chunks < grid) grid = chunks > 0 ? (int)chunks : 1;
+    LaunchScope ls(kTagSqnorm, st);
     sqnorm_kernel<<<grid, kSqThreads, 0, st>>>(tab, partial, counter, out8, per_tensor ? per_tensor + base : nullptr,
                                                base > 0 ? 1 : 0);
     GML_LAUNCH_CHECK();
@@ -214,8 +215,11 @@ extern "C" int gml_squeeze_accumulate(const float* s, const uint8_t* select, int
                                       int64_t* count, void* stream) {
   if (!s || !sum || n < 0 || c <= 0) return GML_E_BADARG;
   if (n == 0) return GML_OK;
-  squeeze_accumulate_kernel<<<ceil_div(c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      s, select, n, c, sum, reinterpret_cast<long long*>(count));
+  {
+    LaunchScope ls(kTagStats, static_cast<cudaStream_t>(stream));
+    squeeze_accumulate_kernel<<<ceil_div(c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        s, select, n, c, sum, reinterpret_cast<long long*>(count));
+  }
   GML_LAUNCH_CHECK();
   return GML_OK;
 }
@@ -223,8 +227,11 @@ extern "C" int gml_squeeze_accumulate(const float* s, const uint8_t* select, int
 extern "C" int gml_accuracy_counts(const float* logits0, const float* logits1, const int64_t* labels, int32_t n,
                                    int32_t k, int32_t* counts3, void* stream) {
   if (!logits0 || !logits1 || !labels || !counts3 || n <= 0 || k <= 0) return GML_E_BADARG;
-  accuracy_counts_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits0, logits1, reinterpret_cast<const long long*>(labels), n, k, counts3);
+  {
+    LaunchScope ls(kTagStats, static_cast<cudaStream_t>(stream));
+    accuracy_counts_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits0, logits1, reinterpret_cast<const long long*>(labels), n, k, counts3);
+  }
   GML_LAUNCH_CHECK();
   return GML_OK;
 }

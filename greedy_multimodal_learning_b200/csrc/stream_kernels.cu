@@ -161,6 +161,7 @@ inline int pick_lanes(int hw, bool vec) {
 
 template <int HW_T, bool VEC, bool DUAL, int EPI>
 int launch_reduce_l(int lanes, const ReduceLaunch& p, int blocks, cudaStream_t st) {
+  LaunchScope ls(DUAL ? kTagDGate : kTagMean, st);
   switch (lanes) {
 #define GML_CASE(LL) \
   case LL: plane_reduce_kernel<LL, HW_T, VEC, DUAL, EPI><<<blocks, kThreads, 0, st>>>(p); break;
@@ -174,6 +175,7 @@ int launch_reduce_l(int lanes, const ReduceLaunch& p, int blocks, cudaStream_t s
 
 template <int HW_T, bool VEC, bool HAS_ADD>
 int launch_scale_l(int lanes, const ScaleLaunch& p, int blocks, cudaStream_t st) {
+  LaunchScope ls(HAS_ADD ? kTagScaleBwd : kTagScaleFwd, st);
   switch (lanes) {
 #define GML_CASE(LL) \
   case LL: plane_scale_kernel<LL, HW_T, VEC, HAS_ADD><<<blocks, kThreads, 0, st>>>(p); break;

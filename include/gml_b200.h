@@ -73,6 +73,19 @@ const char* gml_last_cuda_error(void);
 /* 1 when the running device is compute capability 10.x (B200/B300), else 0; <0 on error */
 int gml_device_is_blackwell(void);
 
+/* Launch accounting (measurement support; bench.py's `gpu_launches` and roofline legs).
+ * gml_launch_count(tag): kernels this library has launched in the process so far, for one
+ * kernel class (0 <= tag < gml_kernel_tag_count()) or all of them (tag < 0).
+ * With profiling enabled every launch is bracketed by CUDA events on its stream;
+ * gml_profile_read drains them (synchronising on the recorded events) and reports the
+ * accumulated device time per class.  Do not enable while capturing a CUDA graph. */
+int64_t gml_launch_count(int tag);
+int gml_kernel_tag_count(void);
+const char* gml_kernel_tag_name(int tag);
+void gml_profile_enable(int on);
+void gml_profile_reset(void);
+int gml_profile_read(int tag, double* total_ms, int64_t* launches);
+
 /* ---------------------------------------------------------------------------------------
  * MMTM forward.  Replaces MMTM_mitigate.forward, src/balanced_mmtm.py:49-154.
  *

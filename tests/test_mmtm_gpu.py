@@ -1,0 +1,293 @@
+"""GPU parity tests for the MMTM kernels: CUDA path (through the Python mirror -> ctypes ->
+C ABI) vs the golden vectors recorded from the reference and vs the CPU oracle.
+
+Tolerance (BASELINE.json north_star): MMTM outputs and gradients within 1e-5 relative, fp32.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import greedy_multimodal_learning_b200 as pkg
+from greedy_multimodal_learning_b200 import _lib
+from oracle import mmtm_oracle as mo
+from tests.golden import make_golden_cases as cases
+from tests.helpers import assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+KEYS = ["A_out", "B_out", "dA", "dB", "gA", "gB", "dWsq", "dbsq", "dWv", "dbv", "dWs", "dbs", "run_v", "run_s"]
+PATHS = {"streaming": _lib.F_FORCE_STREAMING, "auto": 0}
+
+
+def _avg_for(seed, c):
+    rs = np.random.RandomState(seed + 1000)
+    return [torch.from_numpy((0.1 * rs.standard_normal(c)).astype(np.float32)) for _ in range(2)]
+
+
+def make_module(c_v, c_s, params, flags=0, **kw):
+    m = pkg.MMTM_mitigate(c_v, c_s, 4, kernel_flags=flags, **kw)
+    with torch.no_grad():
+        for dst, src in zip((m.fc_squeeze.weight, m.fc_squeeze.bias, m.fc_visual.weight, m.fc_visual.bias,
+                             m.fc_skeleton.weight, m.fc_skeleton.bias), params.tensors()):
+            dst.copy_(src)
+    return m.to(DEV)
+
+
+def mode_kwargs(mode, avg=None):
+    if mode == 1:
+        return dict(curation_mode=True, caring_modality=0)
+    if mode == 2:
+        return dict(curation_mode=True, caring_modality=1)
+    if mode == 3:
+        return dict(turnoff_cross_modal_flow=True, average_squeezemaps=[a.to(DEV) for a in avg])
+    return {}
+
+
+def run_cuda(m, x, mode, avg=None, warm=None):
+    if warm is not None:
+        with torch.no_grad():
+            m(warm["A"].to(DEV), warm["B"].to(DEV))
+    a = x["A"].to(DEV).requires_grad_(True)
+    b = x["B"].to(DEV).requires_grad_(True)
+    for p in m.parameters():
+        p.grad = None
+    a_out, b_out, scales, sq = m(a, b, True, mode != 3, **mode_kwargs(mode, avg))
+    torch.autograd.backward([a_out, b_out], [x["gA"].to(DEV), x["gB"].to(DEV)])
+    g = lambda p: torch.zeros_like(p) if p.grad is None else p.grad
+    out = dict(A_out=a_out, B_out=b_out, dA=a.grad, dB=b.grad, gA=scales[0], gB=scales[1],
+               dWsq=g(m.fc_squeeze.weight), dbsq=g(m.fc_squeeze.bias), dWv=g(m.fc_visual.weight),
+               dbv=g(m.fc_visual.bias), dWs=g(m.fc_skeleton.weight), dbs=g(m.fc_skeleton.bias),
+               run_v=m.running_avg_weight_visual, run_s=m.running_avg_weight_skeleton)
+    out = {k: v.detach().cpu() for k, v in out.items()}
+    out["wv_has_grad"] = m.fc_visual.weight.grad is not None
+    out["ws_has_grad"] = m.fc_skeleton.weight.grad is not None
+    if sq is not None:
+        out["sA"], out["sB"] = sq
+    assert scales[0].device.type == "cpu"  # exports are CPU tensors like the reference's (:118-124)
+    return out
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("case", cases.SMALL_CASES, ids=lambda c: c[0])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_reference_golden_small(case, mode, path):
+    name, n, c, h, w, seed = case
+    gold = np.load(os.path.join(G, "mmtm_small.npz"))
+    x = mo.synth_inputs(seed, n, c, h, w)
+    warm = mo.synth_inputs(seed + 500, n + 1, c, h, w)
+    m = make_module(c, c, mo.synth_params(seed, c, c), PATHS[path])
+    r = run_cuda(m, x, mode, _avg_for(seed, c), warm)
+    for k in KEYS:
+        assert_close(r[k], gold["%s/m%d/%s" % (name, mode, k)], 1e-5, "%s m%d %s" % (name, mode, k))
+    assert m.step == int(gold["%s/m%d/step" % (name, mode)])
+    assert r["wv_has_grad"] == bool(gold["%s/m%d/wv_has_grad" % (name, mode)])
+    assert r["ws_has_grad"] == bool(gold["%s/m%d/ws_has_grad" % (name, mode)])
+    if mode != 3:
+        assert_close(r["sA"], gold["%s/m%d/sA" % (name, mode)], 1e-5, "sA")
+        assert_close(r["sB"], gold["%s/m%d/sB" % (name, mode)], 1e-5, "sB")
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("case", cases.CONFIG_CASES, ids=lambda c: c[0])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_reference_golden_config_shapes(case, mode, path):
+    """128x28^2, 256x14^2, 512x7^2 (N=2): subsamples + checksums recorded from the reference."""
+    name, n, c, h, seed = case
+    gold = np.load(os.path.join(G, "mmtm_config.npz"))
+    x = mo.synth_inputs(seed, n, c, h)
+    warm = mo.synth_inputs(seed + 500, 3, c, h)
+    m = make_module(c, c, mo.synth_params(seed, c, c), PATHS[path])
+    r = run_cuda(m, x, mode, _avg_for(seed, c), warm)
+    for k in KEYS:
+        key = "%s/m%d/%s" % (name, mode, k)
+        v = r[k].numpy()
+        if key in gold.files:
+            assert_close(v, gold[key], 1e-5, key)
+        else:
+            flat = v.reshape(-1)
+            assert_close(flat[::cases.SUB], gold[key + ".sub"], 1e-5, key + ".sub")
+            scale = float(gold[key + ".abssum"])
+            assert abs(flat.astype(np.float64).sum() - float(gold[key + ".sum"])) <= 1e-6 * max(scale, 1e-30)
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+def test_reference_golden_state_sequence(path):
+    """running_avg_* / step across train, no_grad eval and curation calls."""
+    gold = np.load(os.path.join(G, "mmtm_sequence.npz"))
+    c, h, seed = 16, 6, 31
+    m = make_module(c, c, mo.synth_params(seed, c, c), PATHS[path])
+    for i, (mode, n, grad) in enumerate(cases.SEQUENCE):
+        x = mo.synth_inputs(seed + 10 * i, n, c, h)
+        with torch.set_grad_enabled(grad):
+            a_out, b_out, _, _ = m(x["A"].to(DEV), x["B"].to(DEV), **mode_kwargs(mode))
+        assert_close(a_out, gold["%d/A_out" % i], 1e-5, "A_out@%d" % i)
+        assert_close(b_out, gold["%d/B_out" % i], 1e-5, "B_out@%d" % i)
+        assert_close(m.running_avg_weight_visual, gold["%d/run_v" % i], 1e-6, "run_v@%d" % i)
+        assert_close(m.running_avg_weight_skeleton, gold["%d/run_s" % i], 1e-6, "run_s@%d" % i)
+        assert torch.equal(m.running_avg_weight_visual, m.running_avg_weight_skeleton)
+        assert m.step == int(gold["%d/step" % i])
+
+
+# odd / ragged shapes: HW not a multiple of 4, HW = 1, C not a power of two, different C and HW per
+# modality, N = 1, N that is not a multiple of any tile
+ODD = [(1, 3, 5, 1, 1, 1, 1), (5, 7, 7, 3, 3, 2, 5), (3, 20, 12, 7, 7, 5, 5), (9, 32, 32, 10, 5, 10, 5),
+       (2, 6, 10, 4, 4, 9, 9), (33, 64, 64, 13, 13, 13, 13), (4, 128, 128, 28, 28, 28, 28),
+       (130, 24, 24, 6, 6, 6, 6)]
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("shape", ODD, ids=lambda s: "n%dc%dx%d_%dx%d_%dx%d" % s)
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_oracle_parity_odd_shapes(shape, mode, path):
+    n, c_v, c_s, h_v, w_v, h_s, w_s = shape
+    if mode == 2 and c_v != c_s:
+        pytest.skip("reference cannot substitute the skeleton gate when dims differ (balanced_mmtm.py:31)")
+    rs = np.random.RandomState(n * 1000 + c_v)
+    t = lambda *s: torch.from_numpy(rs.standard_normal(s).astype(np.float32))
+    x = dict(A=t(n, c_v, h_v, w_v), B=t(n, c_s, h_s, w_s), gA=t(n, c_v, h_v, w_v), gB=t(n, c_s, h_s, w_s))
+    warm = dict(A=t(2, c_v, h_v, w_v), B=t(2, c_s, h_s, w_s))
+    p = mo.synth_params(5, c_v, c_s)
+    avg = [0.1 * t(c_v), 0.1 * t(c_s)]
+    m = make_module(c_v, c_s, p, PATHS[path])
+    r = run_cuda(m, x, mode, avg, warm)
+    st = mo.MMTMState.zeros(c_v)
+    with torch.no_grad():
+        mo.forward(warm["A"], warm["B"], p, st, 0)
+    o = mo.forward_backward(x["A"], x["B"], p, st, x["gA"], x["gB"], mode, avg)
+    for k in ["A_out", "B_out", "dA", "dB", "gA", "gB", "dWsq", "dbsq", "dWv", "dbv", "dWs", "dbs"]:
+        assert_close(r[k], o[k], 1e-5, k)
+    assert_close(r["run_v"], st.run_v, 1e-6, "run_v")
+
+
+def test_unaligned_pointers_through_the_c_abi():
+    """The C ABI accepts any 4-byte aligned pointer (scalar fallback): offset every buffer by one float."""
+    lib = _lib.load()
+    n, c, hw, d = 3, 8, 12, 8
+    x = mo.synth_inputs(3, n, c, 3, 4)
+    p = mo.synth_params(3, c, c)
+
+    def off(t):  # device copy whose data_ptr is 4 bytes past a 16-byte boundary
+        buf = torch.empty(t.numel() + 1, device=DEV)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.data_ptr() % 16 == 4
+        return v
+
+    a, b = off(x["A"]), off(x["B"])
+    w = [off(t) for t in p.tensors()]
+    a_out, b_out = off(torch.zeros_like(x["A"])), off(torch.zeros_like(x["B"]))
+    z, h = off(torch.zeros(n, 2 * c)), off(torch.zeros(n, d))
+    g_a, g_b, gs = off(torch.zeros(n, c)), off(torch.zeros(n, c)), off(torch.zeros(c))
+    rv, rs_ = off(torch.zeros(c)), off(torch.zeros(c))
+    dims = _lib.MMTMDims(n, c, c, hw, hw, d)
+    P = _lib.ptr
+    _lib.check(lib.gml_mmtm_fwd(P(a), P(b), P(a_out), P(b_out), *[P(t) for t in w], P(z), P(h), P(g_a), P(g_b), P(gs),
+                                P(rv), P(rs_), 0, None, None, None, 0, dims, 0, 1.0, 0,
+                                _lib.current_stream(torch.device(DEV))))
+    o = mo.forward_backward(x["A"], x["B"], p, mo.MMTMState.zeros(c), x["gA"], x["gB"])
+    assert_close(a_out, o["A_out"], 1e-5, "A_out")
+    assert_close(b_out, o["B_out"], 1e-5, "B_out")
+    assert_close(g_a, o["gA"], 1e-5, "gA")
+
+
+def test_c_abi_error_codes():
+    lib = _lib.load()
+    dims = _lib.MMTMDims(2, 8, 8, 4, 4, 8)
+    assert lib.gml_mmtm_apply(None, None, None, None, None, None, None, None, dims, 0, 1.0, None) == -1
+    bad = _lib.MMTMDims(2, 0, 8, 4, 4, 8)
+    t = torch.zeros(1024, device=DEV)
+    p = t.data_ptr()
+    assert lib.gml_mmtm_apply(p, p, p, p, p, p, p, p, bad, 0, 1.0, None) == -1
+    assert lib.gml_mmtm_apply(p, p, p, p, p, p, p, p, dims, 7, 1.0, None) == -1
+    diff = _lib.MMTMDims(2, 8, 4, 4, 4, 6)
+    assert lib.gml_mmtm_apply(p, p, p, p, p, p, p, p, diff, 2, 1.0, None) == -5  # curate skeleton needs c_s == c_v
+    # workspace too small
+    assert lib.gml_mmtm_bwd(*([p] * 23), p, 16, dims, 0, 1.0, 0, None) == -3
+    with pytest.raises(_lib.GmlError, match="workspace"):
+        _lib.check(-3, "x")
+
+
+def test_interface_error_behaviour():
+    m = make_module(8, 8, mo.synth_params(1, 8, 8))
+    a = torch.randn(2, 8, 3, 3, device=DEV)
+    with pytest.raises(RuntimeError):
+        m(a, a, curation_mode=True, caring_modality=None)
+    with pytest.raises(UnboundLocalError):  # reference raises this at balanced_mmtm.py:123-124
+        m(a, a, False, True, turnoff_cross_modal_flow=True, average_squeezemaps=[torch.zeros(8), torch.zeros(8)])
+    with pytest.raises(NotImplementedError):
+        m(a.half(), a.half())
+    assert m.step == 0  # failed calls leave the running state untouched
+
+
+def test_empty_batch_is_a_no_op():
+    m = make_module(8, 8, mo.synth_params(1, 8, 8))
+    a = torch.empty(0, 8, 3, 3, device=DEV)
+    a_out, b_out, _, _ = m(a, a)
+    assert a_out.shape == (0, 8, 3, 3)
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("c,hw", [(128, 28), (256, 14), (512, 7)])
+def test_full_size_properties(c, hw, path):
+    """BASELINE sizes (N=256): size-independent properties instead of an oracle run.
+      * gating identity, bit-exact: A' == A * g (one fp32 multiply, same rounding as torch)
+      * squeeze == torch mean, gates == torch FC chain within fp32 noise
+      * backward is linear in grad_out; dA - grad*g is constant over each plane (= ds/HW)
+      * run-to-run bit reproducibility (no atomics on the data path)
+    """
+    n = 256
+    gen = torch.Generator(device=DEV).manual_seed(c)
+    a = torch.randn(n, c, hw, hw, device=DEV, generator=gen)
+    b = torch.randn(n, c, hw, hw, device=DEV, generator=gen)
+    go_a = torch.randn(n, c, hw, hw, device=DEV, generator=gen)
+    go_b = torch.randn(n, c, hw, hw, device=DEV, generator=gen)
+    p = mo.synth_params(c, c, c)
+    m = make_module(c, c, p, PATHS[path])
+
+    def run(scale=1.0):
+        ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        for q in m.parameters():
+            q.grad = None
+        a_out, b_out, scales, sq = m(ar, br, True, True)
+        torch.autograd.backward([a_out, b_out], [go_a * scale, go_b * scale])
+        return dict(a_out=a_out.detach(), b_out=b_out.detach(), g_a=scales[0].to(DEV), g_b=scales[1].to(DEV),
+                    s_a=sq[0].to(DEV), dA=ar.grad, dB=br.grad, dWsq=m.fc_squeeze.weight.grad.clone(),
+                    dWv=m.fc_visual.weight.grad.clone())
+
+    r1 = run()
+    assert torch.equal(r1["a_out"], a * r1["g_a"][:, :, None, None])
+    assert torch.equal(r1["b_out"], b * r1["g_b"][:, :, None, None])
+    s_ref = a.double().mean(dim=(2, 3))
+    assert rel_err(r1["s_a"], s_ref) < 2e-6
+    with torch.no_grad():
+        z = torch.cat([a.mean(dim=(2, 3)), b.mean(dim=(2, 3))], 1).double()
+        hdn = torch.relu(z @ m.fc_squeeze.weight.double().T + m.fc_squeeze.bias.double())
+        g_ref = torch.sigmoid(hdn @ m.fc_visual.weight.double().T + m.fc_visual.bias.double())
+    assert rel_err(r1["g_a"], g_ref) < 1e-5
+    # plane-constant residual
+    resid = r1["dA"] - go_a * r1["g_a"][:, :, None, None]
+    spread = (resid.amax(dim=(2, 3)) - resid.amin(dim=(2, 3))).max()
+    assert float(spread) <= 1e-5 * float(go_a.abs().max())
+    # linearity
+    r2 = run(2.0)
+    assert rel_err(r2["dA"], 2 * r1["dA"]) < 1e-6 and rel_err(r2["dWsq"], 2 * r1["dWsq"]) < 1e-6
+    # determinism
+    r3 = run()
+    for k in ("a_out", "dA", "dB", "dWsq", "dWv", "g_a"):
+        assert torch.equal(r1[k], r3[k]), k
+
+
+def test_gate_scale_two_sigma_option():
+    """north_star mentions 2*sigmoid gating (original MMTM); reference code uses 1*sigmoid.
+    gate_scale=2 must equal the oracle with gate_scale=2."""
+    n, c, hw = 3, 16, 5
+    x = mo.synth_inputs(9, n, c, hw)
+    p = mo.synth_params(9, c, c)
+    m = make_module(c, c, p, gate_scale=2.0)
+    r = run_cuda(m, x, 0)
+    o = mo.forward_backward(x["A"], x["B"], p, mo.MMTMState.zeros(c), x["gA"], x["gB"], 0, None, 2.0)
+    for k in ["A_out", "B_out", "dA", "dB", "dWsq", "dWv", "dWs"]:
+        assert_close(r[k], o[k], 1e-5, k)

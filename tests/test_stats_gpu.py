@@ -1,0 +1,241 @@
+"""GPU parity tests for the analysis statistics: conditional learning speed (multi-tensor
+sqnorm + controller), conditional-utilization squeeze means, accuracy counts, and the
+end-to-end guided-training trace.
+
+Tolerances (BASELINE.json north_star): statistics within 1e-6 relative; argmax/accuracy
+counts bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import greedy_multimodal_learning_b200 as pkg
+from greedy_multimodal_learning_b200 import _lib
+from oracle import mmtm_oracle as mo
+from oracle import stats_oracle as so
+from oracle.mmtm_module import OracleMMTM
+from tests.golden import make_golden_cases as cases
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+BR, MM = ["net_view_0", "net_view_1"], ["visual", "skeleton"]
+
+
+def _sqnorm_raw(tensors, masks, kinds):
+    import ctypes
+    lib = _lib.load()
+    n = len(tensors)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    numel = (ctypes.c_int64 * n)(*[t.numel() for t in tensors])
+    m = (ctypes.c_int32 * n)(*masks)
+    k = (ctypes.c_int32 * n)(*kinds)
+    ws_bytes = lib.gml_sqnorm_workspace_bytes(numel, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    out = torch.full((8,), -1.0, dtype=torch.float64, device=DEV)
+    per = torch.full((n,), -1.0, dtype=torch.float64, device=DEV)
+    _lib.check(lib.gml_multi_tensor_sqnorm(ptrs, numel, m, k, n, out.data_ptr(), per.data_ptr(), ws.data_ptr(),
+                                           ws_bytes, _lib.current_stream(torch.device(DEV))))
+    return out.cpu().numpy(), per.cpu().numpy()
+
+
+def test_sqnorm_ragged_sizes_and_alignment():
+    rs = np.random.RandomState(0)
+    sizes = [1, 3, 4, 5, 255, 4095, 4096, 4097, 8192, 100003, 1 << 20, 0, 7]
+    tensors, masks, kinds = [], [], []
+    for i, s in enumerate(sizes):
+        buf = torch.from_numpy(rs.standard_normal(s + 3).astype(np.float32)).to(DEV)
+        tensors.append(buf[i % 4: i % 4 + s])  # every misalignment 0, 4, 8, 12 bytes
+        masks.append((1, 2, 4, 8, 12, 3)[i % 6])
+        kinds.append(i % 2)
+    out, per = _sqnorm_raw(tensors, masks, kinds)
+    want = np.zeros(8)
+    for i, t in enumerate(tensors):
+        s64 = float((t.double() ** 2).sum())
+        assert abs(per[i] - s64) <= 1e-6 * max(s64, 1e-30), (i, sizes[i])
+        for bit in range(4):
+            if masks[i] & (1 << bit):
+                want[kinds[i] * 4 + bit] += s64
+    np.testing.assert_allclose(out, want, rtol=1e-6)
+    out2, per2 = _sqnorm_raw(tensors, masks, kinds)
+    assert np.array_equal(out, out2) and np.array_equal(per, per2)  # fixed reduction order
+
+
+def test_sqnorm_more_tensors_than_one_launch_holds():
+    rs = np.random.RandomState(1)
+    tensors = [torch.from_numpy(rs.standard_normal(17 + i % 5).astype(np.float32)).to(DEV) for i in range(1500)]
+    masks = [1 + (i % 3 == 0) * 4 for i in range(1500)]
+    kinds = [i % 2 for i in range(1500)]
+    out, per = _sqnorm_raw(tensors, masks, kinds)
+    want = np.zeros(8)
+    for t, m, k in zip(tensors, masks, kinds):
+        s = float((t.double() ** 2).sum())
+        for bit in range(4):
+            if m & (1 << bit):
+                want[k * 4 + bit] += s
+    np.testing.assert_allclose(out, want, rtol=1e-6)
+
+
+def test_learning_speed_on_the_real_model_matches_oracle():
+    """All 142 parameters + gradients of MMTM_MVCNN in one launch vs the oracle's per-tensor
+    loop (callbacks.py:203-223) on the same values."""
+    torch.manual_seed(777)
+    model = pkg.MMTM_MVCNN().to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    for p in model.parameters():
+        p.grad = torch.randn(p.shape, device=DEV, generator=gen) * 0.01
+    sq = pkg.MultiTensorSqnorm(model.named_parameters(), BR, MM)
+    got = sq.measure()
+    want = so.sqnorm_buckets(((n, p.detach().cpu(), p.grad.cpu()) for n, p in model.named_parameters()), BR, MM)
+    for k in want:
+        for i in (0, 1):
+            assert abs(got[k][i] - want[k][i]) <= 1e-6 * want[k][i], (k, i, got[k][i], want[k][i])
+    # d_BDR through the callback equals the oracle's accumulator on the same buckets
+    cb = pkg.Bias_Mitigation_Strong(0.01, 5, BR, 1)
+    cb.set_model(model, ignore=False)
+
+    class MP:
+        pass
+
+    cb.set_model_pytoune(MP())
+    cb.on_train_begin({})
+    ls = so.LearningSpeed()
+    for _ in range(3):
+        d = cb.compute_BDR()
+        d_ref = ls.update(want)
+        assert abs(d - d_ref) <= 1e-6 * max(abs(d_ref), 1e-3)
+    # gradients re-allocated (zero_grad(set_to_none=True)) -> table is rebuilt transparently
+    for p in model.parameters():
+        p.grad = None
+    with pytest.raises(RuntimeError):
+        sq.measure()
+    for p in model.parameters():
+        p.grad = torch.ones_like(p)
+    got2 = sq.measure()
+    assert abs(got2["gn_main"][0] - 11_197_032) < 1e-3  # 62 tensors, 11,197,032 elements
+    assert abs(got2["gn_bypass"][1] - 1_033_984) < 1e-3
+
+
+def test_accuracy_counts_bit_exact():
+    rs = np.random.RandomState(5)
+    for n, k in ((1, 40), (2, 40), (3, 5), (8, 40), (256, 40), (1000, 7)):
+        l0 = rs.standard_normal((n, k)).astype(np.float32)
+        l1 = rs.standard_normal((n, k)).astype(np.float32)
+        if n >= 3:
+            l0[1, 2] = l0[1, k - 1] = l0[1].max() + 1  # exact tie: first index wins
+        y = rs.randint(0, k, size=n).astype(np.int64)
+        y[0] = int(np.argmax(l0[0]))
+        t0, t1, ty = torch.from_numpy(l0), torch.from_numpy(l1), torch.from_numpy(y)
+        counts = torch.empty(3, dtype=torch.int32, device=DEV)
+        lib = _lib.load()
+        _lib.check(lib.gml_accuracy_counts(t0.to(DEV).data_ptr(), t1.to(DEV).data_ptr(), ty.to(DEV).data_ptr(), n, k,
+                                           counts.data_ptr(), _lib.current_stream(torch.device(DEV))))
+        want = [so.correct_count((t0 + t1) / 2, ty)[0], so.correct_count(t0, ty)[0], so.correct_count(t1, ty)[0]]
+        assert counts.tolist() == want, (n, k)
+
+
+def test_squeeze_mean_recorder_matches_get_rescale_weights():
+    """Recording pass on device (no per-batch D2H) == the reference's pickle round trip."""
+    ev, tr = cases.synth_history()
+    dims = (8, 12, 16)
+
+    class Blk:  # stands in for three MMTM blocks: only dims + last_squeeze are used
+        def __init__(self, d):
+            self.dim_visual, self.dim_skeleton = d, d
+
+    blocks = [Blk(d) for d in dims]
+    rec = pkg.SqueezeMeanRecorder(blocks, selected_indices=tr["train_indices"][0])
+    pos = 0
+    for batch in ev["test_squeezedmaps_array_list"][0]:
+        nb = batch[0][0].shape[0]
+        idx = ev["test_indices"][0][pos:pos + nb]
+        pos += nb
+        for blk, views in zip(blocks, batch):
+            blk.last_squeeze = torch.cat([views[0], views[1]], 1).to(DEV).contiguous()
+        rec.update(idx)
+    got = rec.result(device="cpu")
+    want = so.mean_squeezes_from_history(ev, tr)
+    assert got[0] is None and len(got) == 4
+    for p in (1, 2, 3):
+        for v in (0, 1):
+            assert_close(got[p][v], want[p][v], 1e-6, "pos%d view%d" % (p, v))
+
+
+def test_utilization_pipeline_recording_then_flow_cut():
+    """recording.gin -> eval.gin in miniature on the real model: recorded squeezes (exported
+    CPU tensors, reference layout) give the same dataset means as the on-device recorder, and
+    the mmtm_off forward with those means matches the oracle model."""
+    torch.manual_seed(777)
+    model = pkg.MMTM_MVCNN(saving_mmtm_squeeze_array=True).to(DEV).eval()
+    loader = cases.synth_loader(71, 3, 4, 64)
+    rec = pkg.SqueezeMeanRecorder(model.mmtm_blocks())
+    batches, indices = [], []
+    with torch.no_grad():
+        for idx, x, y in loader:
+            _, _, _, sq = model(x.to(DEV))
+            batches.append(sq)
+            indices.append(idx.numpy())
+            rec.update(idx)
+    ev = {"test_squeezedmaps_array_list": [batches], "test_indices": [np.concatenate(indices)]}
+    tr = {"train_indices": [np.arange(12)]}
+    want = so.mean_squeezes_from_history(ev, tr)
+    got = rec.result(device=DEV)
+    for p in (1, 2, 3):
+        for v in (0, 1):
+            assert_close(got[p][v], want[p][v], 1e-6, "mean squeeze")
+    torch.manual_seed(777)
+    off = pkg.MMTM_MVCNN(mmtm_off=True, mmtm_rescale=got).to(DEV).eval()
+    torch.manual_seed(777)
+    ref = pkg.MMTM_MVCNN(mmtm_off=True, mmtm_rescale=[None] + [[t.cpu() for t in w] for w in got[1:]],
+                         mmtm_cls=OracleMMTM).eval()
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        idx, x, y = loader[0]
+        y_gpu = off(x.to(DEV))
+        y_cpu = ref(x)
+    assert_close(y_gpu[0], y_cpu[0], 2e-4, "fused logits with cross-modal flow cut")
+    k_gpu = [so.correct_count(t.cpu(), y)[0] for t in y_gpu[1]]
+    k_cpu = [so.correct_count(t, y)[0] for t in y_cpu[1]]
+    assert k_gpu == k_cpu
+
+
+def test_guided_training_trace_on_gpu():
+    """Full hot path on the GPU (CUDA MMTM fwd/bwd, multi-tensor sqnorm, device accuracy counts,
+    cuDNN backbone with TF32 off) vs the trace recorded from the reference's training_loop on CPU.
+    Controller decisions and accuracy counts must agree exactly; losses / d_BDR within the
+    accumulated fp32 noise of a different convolution backend."""
+    g = json.load(open(os.path.join(G, "guided_trace.json")))
+    if g["torch"] != torch.__version__:
+        pytest.skip("golden trace was recorded with torch %s" % g["torch"])
+    cfg = g["cfg"]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(cfg["seed"])
+    model = pkg.MMTM_MVCNN()
+    opt = torch.optim.SGD(model.parameters(), lr=cfg["lr"], weight_decay=0.0, momentum=0)
+    cb = pkg.Bias_Mitigation_Strong(cfg["epsilon"], cfg["window"], BR, cfg["starting_epoch"])
+    cb.set_model(model, ignore=False)
+    got = []
+
+    class Rec(pkg.Callback):
+        def on_batch_end(self, batch, logs):
+            got.append(dict(logs))
+
+    engine = pkg.Model_(model, opt, pkg.blend_loss, 2, metrics=[pkg.acc]).to(torch.device(DEV))
+    tr = cases.synth_loader(cfg["data_seed"], cfg["train_batches"], cfg["batch"], cfg["image"])
+    va = cases.synth_loader(cfg["data_seed"] + 1, cfg["val_batches"], cfg["batch"], cfg["image"], 1000)
+    te = cases.synth_loader(cfg["data_seed"] + 2, cfg["test_batches"], cfg["batch"], cfg["image"], 2000)
+    engine.train_loop(tr, valid_generator=va, test_generator=te, epochs=cfg["n_epochs"] - 1, steps_per_epoch=len(tr),
+                      validation_steps=len(va), test_steps=len(te), callbacks=[cb, Rec()])
+    want = [t for t in g["trace"] if t["kind"] == "batch"]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a["curation_mode"] == b["curation_mode"] and a["caring_modality"] == b["caring_modality"]
+        assert a["acc"] == b["acc"] and a["acc_modal_0"] == b["acc0"] and a["acc_modal_1"] == b["acc1"]
+        assert abs(a["loss"] - b["loss"]) <= 2e-3 * abs(b["loss"]), (a["loss"], b["loss"])
+        assert abs(a["d_BDR"] - b["d_BDR"]) <= 2e-3 * max(1e-2, abs(b["d_BDR"])), (a["d_BDR"], b["d_BDR"])
+    assert [m.step for m in model.mmtm_blocks()] == g["final"]["mmtm_step"]
