@@ -207,6 +207,9 @@ class MMTM_mitigate(nn.Module):
         if mode == MODE_XMODAL_OFF:
             m_a = average_squeezemaps[0].detach().to(device=dev, dtype=torch.float32).contiguous()
             m_b = average_squeezemaps[1].detach().to(device=dev, dtype=torch.float32).contiguous()
+        if visual.shape[0] == 0:
+            # empty batch: nothing to launch (the reference would produce NaN running means here)
+            return visual.clone(), skeleton.clone(), None, None
         a, b = visual.contiguous(), skeleton.contiguous()
         # the reference rebinds running_avg_* to fresh tensors every call (:113-114); keep that
         # aliasing behaviour (a caller holding the old tensor does not see it change)

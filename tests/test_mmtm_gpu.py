@@ -162,6 +162,48 @@ def test_oracle_parity_odd_shapes(shape, mode, path):
     assert_close(r["run_v"], st.run_v, 1e-6, "run_v")
 
 
+# shapes the cluster / shared-memory-resident kernels accept (forced: GML_F_FORCE_FUSED fails loudly
+# instead of falling back): partial last group (odd N with 2 samples per group), fewer groups than
+# clusters, many rounds per cluster (prefetch of the next group), single chunk, large planes
+FUSED = [(1, 16, 4, 4), (2, 16, 4, 4), (3, 32, 8, 8), (5, 64, 6, 6), (7, 128, 28, 28), (9, 256, 14, 14),
+         (150, 128, 28, 28), (301, 256, 14, 14), (40, 64, 16, 16)]
+
+
+@pytest.mark.parametrize("shape", FUSED, ids=lambda s: "n%dc%d_%dx%d" % s)
+def test_fused_cluster_kernels_vs_oracle(shape):
+    n, c, h, w = shape
+    rs = np.random.RandomState(n * 7 + c)
+    t = lambda *s: torch.from_numpy(rs.standard_normal(s).astype(np.float32))
+    x = dict(A=t(n, c, h, w), B=t(n, c, h, w), gA=t(n, c, h, w), gB=t(n, c, h, w))
+    p = mo.synth_params(c + n, c, c)
+    m = make_module(c, c, p, _lib.F_FORCE_FUSED)
+    lib = _lib.load()
+    before = lib.gml_launch_count(6) + lib.gml_launch_count(7)
+    r = run_cuda(m, x, 0)
+    assert lib.gml_launch_count(6) + lib.gml_launch_count(7) == before + 2  # one fused fwd + one fused bwd
+    st = mo.MMTMState.zeros(c)
+    o = mo.forward_backward(x["A"], x["B"], p, st, x["gA"], x["gB"], 0)
+    for k in ["A_out", "B_out", "dA", "dB", "gA", "gB", "sA", "sB", "dWsq", "dbsq", "dWv", "dbv", "dWs", "dbs"]:
+        assert_close(r[k], o[k], 1e-5, k)
+    assert_close(r["run_v"], st.run_v, 1e-6, "run_v")
+    # streaming and fused paths agree to fp32 rounding and are each bit-reproducible
+    m2 = make_module(c, c, p, _lib.F_FORCE_STREAMING)
+    r2 = run_cuda(m2, x, 0)
+    for k in ["A_out", "dA", "dWsq"]:
+        assert rel_err(r[k], r2[k]) < 2e-6, k
+    m3 = make_module(c, c, p, _lib.F_FORCE_FUSED)
+    r3 = run_cuda(m3, x, 0)
+    for k in ["A_out", "B_out", "dA", "dB", "dWsq", "dWv", "gA"]:
+        assert torch.equal(r[k], r3[k]), k
+
+
+def test_force_fused_fails_loudly_when_unsupported():
+    m = make_module(24, 24, mo.synth_params(1, 24, 24), _lib.F_FORCE_FUSED)
+    a = torch.randn(2, 24, 5, 5, device=DEV)
+    with pytest.raises(_lib.GmlError, match="unsupported"):
+        m(a, a)
+
+
 def test_unaligned_pointers_through_the_c_abi():
     """The C ABI accepts any 4-byte aligned pointer (scalar fallback): offset every buffer by one float."""
     lib = _lib.load()
