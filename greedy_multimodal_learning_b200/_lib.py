@@ -41,6 +41,7 @@ SIGNATURES = {
     "gml_profile_enable": (None, [c_int]),
     "gml_profile_reset": (None, []),
     "gml_profile_read": (c_int, [c_int, POINTER(c_double), POINTER(c_int64)]),
+    "gml_set_tunable": (c_int, [c_char_p, c_int64]),
     "gml_mmtm_fwd_workspace_bytes": (c_size_t, [POINTER(MMTMDims)]),
     "gml_mmtm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P,
                              c_size_t, POINTER(MMTMDims), c_int, c_float, c_uint32, _P]),

@@ -91,14 +91,16 @@ int check_dims(const gml_mmtm_dims* in, int mode, Dims* o) {
 // How many samples to push through both passes before moving on, so that the second pass
 // (gating / gradient apply) re-reads its input from L2 instead of HBM.  B200 has ~126 MB of L2;
 // the default budget leaves room for the output lines that are being written back.
+std::atomic<long> g_l2_chunk_mb{-1};
 size_t l2_budget_bytes() {
-  static size_t v = [] {
+  long mb = g_l2_chunk_mb.load();
+  if (mb < 0) {
     const char* e = getenv("GML_L2_CHUNK_MB");
-    long mb = e ? atol(e) : 40;
+    mb = e ? atol(e) : 40;
     if (mb < 1) mb = 1;
-    return (size_t)mb << 20;
-  }();
-  return v;
+    g_l2_chunk_mb.store(mb);
+  }
+  return (size_t)mb << 20;
 }
 
 int chunk_samples(const Dims& d, size_t bytes_per_sample) {
@@ -209,6 +211,24 @@ extern "C" int gml_profile_read(int tag, double* total_ms, int64_t* launches) {
   *total_ms = g_prof_ms[tag];
   *launches = g_prof_n[tag];
   return GML_OK;
+}
+
+namespace gml {
+extern int g_fused_cluster;
+extern int g_fused_threads;
+}
+extern "C" int gml_set_tunable(const char* name, int64_t value) {
+  if (!name) return GML_E_BADARG;
+  if (!strcmp(name, "l2_chunk_mb")) { g_l2_chunk_mb.store(value < 1 ? 1 : (long)value); return GML_OK; }
+  if (!strcmp(name, "fused_cluster")) {
+    if (value != 0 && value != 4 && value != 8) return GML_E_BADARG;
+    g_fused_cluster = (int)value; return GML_OK;
+  }
+  if (!strcmp(name, "fused_threads")) {
+    if (value != 0 && value != 256 && value != 512) return GML_E_BADARG;
+    g_fused_threads = (int)value; return GML_OK;
+  }
+  return GML_E_BADARG;
 }
 
 extern "C" int gml_device_is_blackwell(void) {

@@ -3,17 +3,19 @@
 // u = N*C*HW*4 B per modality) instead of the 6u / 8u of the streaming two-pass path.
 //
 // Layout of the work
-//   * a cluster of 4 CTAs (1 CTA per SM, ~210 KB dynamic shared memory each) owns a group of G
-//     samples; CTA r holds channels [r*C/4, (r+1)*C/4) of BOTH modalities of those samples:
-//     G * 2 * (C/4) planes of HW floats = 200,704 B for 128x28^2 (G=1) and 256x14^2 (G=2).
+//   * a cluster of CS CTAs owns a group of G samples; CTA r holds channels [r*C/CS, (r+1)*C/CS)
+//     of BOTH modalities of those samples.  Two geometries:
+//       CS = 4, one  CTA per SM, ~200 KB of planes per CTA   (128x28^2: G=1, 256x14^2: G=2)
+//       CS = 8, two CTAs per SM, ~100 KB of planes per CTA   (same G) -- the second resident CTA
+//               streams while the first one sits in its FC / cluster-barrier phase
 //   * the CTA's planes arrive as NCHUNK 1-D TMA bulk copies (cp.async.bulk, contiguous in NCHW),
 //     each signalling its own mbarrier: the reduction pass consumes chunks as they land, and
 //     while the output pass drains chunk j to HBM the NEXT group's chunk j is already being
 //     fetched into the freed space (loads and stores overlap inside one CTA).
 //   * the squeeze vector (2C floats per sample) and the hidden state (D floats) are exchanged
-//     through distributed shared memory (every CTA writes its part into all four CTAs), two
-//     cluster barriers per group; the FCs are per-sample GEMVs on CUDA cores with the weights
-//     streamed from L2 (4C^2 floats per group: 0.16x / 0.65x of the group's HBM bytes).
+//     through distributed shared memory (every CTA writes its part into all CTAs of the cluster),
+//     two cluster barriers per group; the FCs are per-sample GEMVs on CUDA cores, weights streamed
+//     from L2 with several rows in flight per warp (latency, not bandwidth, is what matters there).
 //   * persistent: clusters loop over groups with stride = number of resident clusters.
 // Forward: resident = inputs.  Backward: resident = grad_out (needed twice: dot, then apply);
 // the saved inputs stream through registers once for the dot.  Weight gradients are NOT formed
@@ -23,6 +25,10 @@
 // Shapes outside the supported set fall back to the streaming kernels (capi.cu).
 #include <cooperative_groups.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,18 +36,21 @@ namespace cg = cooperative_groups;
 
 namespace gml {
 
+int g_fused_cluster = 0;   // tunables (gml_set_tunable): 0 = automatic
+int g_fused_threads = 0;
+
 namespace {
 
-constexpr int kCluster = 4;
-constexpr int kThreadsF = 256;
-constexpr int kWarpsF = kThreadsF / 32;
+constexpr int kMaxCluster = 8;
 constexpr int kMaxChunks = 16;
-constexpr size_t kDataBudget = 204800;  // bytes of resident planes per CTA
+constexpr int kRowsPerBatch = 4;  // GEMV rows a warp keeps in flight at once
 
 struct FusedCfg {
   int n, c, hw, d;
+  int cs;        // CTAs per cluster
+  int threads;   // threads per CTA
   int g;         // samples per group
-  int cq, dq;    // C/4, D/4
+  int cq, dq;    // C/cs, D/cs
   int pl;        // planes per CTA = g * 2 * cq
   int pc;        // planes per chunk
   int nchunk;    // pl / pc
@@ -87,31 +96,34 @@ struct Smem {
   float* psum;    // [pl] plane sums / dots
   float* scale;   // [pl] per-plane multiplier of the output pass
   float* addv;    // [pl] per-plane additive term (backward)
-  float* vec_a;   // [g][2C]  z (fwd) / dE (bwd), full vector, filled by all 4 CTAs
+  float* bias_h;  // [dq]      my slice of b_sq
+  float* bias_g;  // [2][cq]   my slices of b_v, b_s
+  float* vec_a;   // [g][2C]  z (fwd) / dE (bwd), full vector, filled by all CTAs of the cluster
   float* vec_b;   // [g][D]   h (fwd) / dH (bwd)
   float* part;    // cross-warp partial sums of the transposed GEMVs (backward)
 };
 
-__device__ __forceinline__ Smem carve(unsigned char* base, const FusedCfg& f, bool bwd) {
+__host__ __device__ inline size_t extras_bytes(const FusedCfg& f, bool bwd) {
+  size_t b = kMaxChunks * sizeof(uint64_t) + 3 * (size_t)f.pl * 4 + ((size_t)f.dq + 2 * f.cq) * 4 +
+             (size_t)f.g * 2 * f.c * 4 + (size_t)f.g * f.d * 4;
+  if (bwd) b += (size_t)f.threads * f.g * 4;  // part[slices][g][cols], slices * cols == threads
+  return b + 16;
+}
+
+__device__ __forceinline__ Smem carve(unsigned char* base, const FusedCfg& f) {
   Smem s;
   s.data = reinterpret_cast<float*>(base);
   unsigned char* p = base + f.data_bytes;
   s.bars = reinterpret_cast<uint64_t*>(p); p += kMaxChunks * sizeof(uint64_t);
+  s.vec_a = reinterpret_cast<float*>(p); p += (size_t)f.g * 2 * f.c * sizeof(float);   // 16-byte aligned
+  s.vec_b = reinterpret_cast<float*>(p); p += (size_t)f.g * f.d * sizeof(float);       // 16-byte aligned
   s.psum = reinterpret_cast<float*>(p); p += f.pl * sizeof(float);
   s.scale = reinterpret_cast<float*>(p); p += f.pl * sizeof(float);
   s.addv = reinterpret_cast<float*>(p); p += f.pl * sizeof(float);
-  s.vec_a = reinterpret_cast<float*>(p); p += (size_t)f.g * 2 * f.c * sizeof(float);
-  s.vec_b = reinterpret_cast<float*>(p); p += (size_t)f.g * f.d * sizeof(float);
+  s.bias_h = reinterpret_cast<float*>(p); p += f.dq * sizeof(float);
+  s.bias_g = reinterpret_cast<float*>(p); p += 2 * f.cq * sizeof(float);
   s.part = reinterpret_cast<float*>(p);
-  (void)bwd;
   return s;
-}
-
-size_t smem_bytes(const FusedCfg& f, bool bwd) {
-  size_t b = f.data_bytes + kMaxChunks * sizeof(uint64_t) + 3 * (size_t)f.pl * 4 + (size_t)f.g * 2 * f.c * 4 +
-             (size_t)f.g * f.d * 4;
-  if (bwd) b += (size_t)kThreadsF * f.g * 4;  // part[slices][g][outs], slices * outs == 256
-  return b + 16;
 }
 
 // plane p of this CTA -> (sample in group, modality, local channel)
@@ -137,40 +149,58 @@ __device__ __forceinline__ void issue_chunks(const FusedCfg& f, const Smem& s, c
   }
 }
 
-// y[row] = <W[row0 + row, 0:K], x[g, 0:K]> for rows handled warp-per-row, K % 4 == 0
-template <int GMAX, typename Epi>
-__device__ __forceinline__ void gemv_rows(const float* __restrict__ w, int ldw, int row0, int nrows, int k,
-                                          const float* x, int ldx, int gcount, Epi epi) {
+// y[row] = <W[row0 + row, 0:K], x[g, 0:K]>, K % 4 == 0.  Each warp owns kRowsPerBatch rows at a time
+// and issues all their weight loads before the first FMA (the weights come from L2: the cost is
+// latency, so several rows must be in flight); lane r then finishes row r.
+template <int T, int GMAX, typename RowPtr, typename Epi>
+__device__ __forceinline__ void gemv_rows(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
+                                          Epi epi) {
+  constexpr int R = kRowsPerBatch;
+  constexpr int kWarps = T / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k4 = k >> 2;
-  for (int r = warp; r < nrows; r += kWarpsF) {
-    const float4* wr = reinterpret_cast<const float4*>(w + (size_t)(row0 + r) * ldw);
-    float acc[GMAX];
+  for (int base = warp * R; base < nrows; base += kWarps * R) {
+    float acc[R][GMAX];
 #pragma unroll
-    for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int g = 0; g < GMAX; ++g) acc[r][g] = 0.f;
+#pragma unroll 2
     for (int i = lane; i < k4; i += 32) {
-      const float4 wv = __ldg(wr + i);
+      float4 wv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = min(base + r, nrows - 1);  // clamp: duplicates are discarded in the epilogue
+        wv[r] = __ldg(reinterpret_cast<const float4*>(rowptr(row)) + i);
+      }
 #pragma unroll
       for (int g = 0; g < GMAX; ++g) {
         if (g < gcount) {
           const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)g * ldx + 4 * i);
-          acc[g] = fmaf(wv.x, xv.x, acc[g]); acc[g] = fmaf(wv.y, xv.y, acc[g]);
-          acc[g] = fmaf(wv.z, xv.z, acc[g]); acc[g] = fmaf(wv.w, xv.w, acc[g]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r][g] = fmaf(wv[r].x, xv.x, acc[r][g]); acc[r][g] = fmaf(wv[r].y, xv.y, acc[r][g]);
+            acc[r][g] = fmaf(wv[r].z, xv.z, acc[r][g]); acc[r][g] = fmaf(wv[r].w, xv.w, acc[r][g]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int g = 0; g < GMAX; ++g) acc[g] = warp_sum(acc[g]);
-    if (lane == 0) epi(r, acc);
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int g = 0; g < GMAX; ++g) acc[r][g] = warp_sum(acc[r][g]);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (lane == r && base + r < nrows) epi(base + r, acc[r]);
   }
 }
 
-// y[col] = sum_k x[g, k] * W[k, col0 + col] (transposed GEMV): thread = (k-slice, col), coalesced in col.
-// Partials go to s_part[slice][g][col]; the caller reduces the slices in a fixed order.
-template <int GMAX>
+// y[col] = sum_k x[g, k] * W[k, col0 + col] (transposed GEMV): thread = (k-slice, col), coalesced in
+// col.  Partials are ADDED into s_part[slice][g][col]; the caller reduces the slices in a fixed order.
+template <int T, int GMAX>
 __device__ __forceinline__ void gemv_cols_partial(const float* __restrict__ w, int ldw, int col0, int ncols, int k0,
                                                   int k1, const float* x, int ldx, int gcount, float* s_part) {
-  const int slices = kThreadsF / ncols;
+  const int slices = T / ncols;
   const int col = threadIdx.x % ncols, sl = threadIdx.x / ncols;
   const int span = (k1 - k0 + slices - 1) / slices;
   const int ka = k0 + sl * span, kb = min(k1, ka + span);
@@ -178,7 +208,7 @@ __device__ __forceinline__ void gemv_cols_partial(const float* __restrict__ w, i
 #pragma unroll
   for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
   const float* wp = w + col0 + col;
-#pragma unroll 4
+#pragma unroll 16
   for (int kk = ka; kk < kb; ++kk) {
     const float wv = __ldg(wp + (size_t)kk * ldw);
 #pragma unroll
@@ -189,35 +219,45 @@ __device__ __forceinline__ void gemv_cols_partial(const float* __restrict__ w, i
   for (int g = 0; g < GMAX; ++g) s_part[((size_t)sl * GMAX + g) * ncols + col] += acc[g];
 }
 
-// =============================================================================================
-// forward
-// =============================================================================================
-template <int L, int GMAX>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
-    fused_fwd_kernel(const FusedFwdArgs a, const FusedCfg f) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int cluster_id = blockIdx.x / kCluster, n_clusters = gridDim.x / kCluster;
-  const Smem s = carve(smem_raw, f, false);
+template <int T>
+__device__ __forceinline__ void common_prologue(const FusedCfg& f, const Smem& s, const float* b_sq, const float* b_v,
+                                                const float* b_s, int rank) {
   const int tid = threadIdx.x;
-  const uint64_t pol_stream = policy_evict_first();
-
   if (tid == 0) {
     for (int j = 0; j < f.nchunk; ++j) mbar_init(&s.bars[j], 1);
     fence_mbar_init();
   }
+  if (b_sq) {
+    for (int i = tid; i < f.dq; i += T) s.bias_h[i] = __ldg(b_sq + rank * f.dq + i);
+    for (int i = tid; i < 2 * f.cq; i += T)
+      s.bias_g[i] = __ldg((i < f.cq ? b_v : b_s) + rank * f.cq + (i < f.cq ? i : i - f.cq));
+  }
   __syncthreads();
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int T, int L, int GMAX>
+__global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const FusedFwdArgs a, const FusedCfg f) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / f.cs, n_clusters = gridDim.x / f.cs;
+  const Smem s = carve(smem_raw, f);
+  const int tid = threadIdx.x;
+  const uint64_t pol_stream = policy_evict_first();
+
+  common_prologue<T>(f, s, a.b_sq, a.b_v, a.b_s, rank);
   if (tid == 0 && cluster_id < f.n_groups) {
     const int n0 = cluster_id * f.g;
     issue_chunks(f, s, a.a, a.b, rank, n0, min(f.g, f.n - n0), 0, f.nchunk, pol_stream);
   }
   cluster.sync();  // every CTA of the cluster is alive before anyone writes remote shared memory
 
-  constexpr int kPlanesPerPass = kThreadsF / L;
+  constexpr int kPlanesPerPass = T / L;
   const int lane = tid % L, grp_in_pass = tid / L;
   const int hw4 = f.hw >> 2;
-  const float inv_gate_scale_unused = 0.f; (void)inv_gate_scale_unused;
   uint32_t parity = 0;
 
   for (int grp = cluster_id; grp < f.n_groups; grp += n_clusters) {
@@ -244,45 +284,44 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
     }
     __syncthreads();
     // ---- squeeze vector -> every CTA of the cluster (DSMEM) + global z ------------------------
-    for (int p = tid; p < vplanes; p += kThreadsF) {
+    for (int p = tid; p < vplanes; p += T) {
       int g, mod, cl;
       plane_coords(f, p, g, mod, cl);
       const int k = mod * f.c + rank * f.cq + cl;
       const float mean = s.psum[p] / (float)f.hw;
-#pragma unroll
-      for (int dst = 0; dst < kCluster; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + k] = mean;
+      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + k] = mean;
       a.z[(size_t)(n0 + g) * 2 * f.c + k] = mean;
     }
     cluster.sync();
-    // ---- FC1: my quarter of the hidden units, H = relu(Wsq z + bsq) ---------------------------
-    gemv_rows<GMAX>(a.w_sq, 2 * f.c, rank * f.dq, f.dq, 2 * f.c, s.vec_a, 2 * f.c, gcount,
-                    [&](int r, const float* acc) {
-                      const int dd = rank * f.dq + r;
-                      const float bias = __ldg(a.b_sq + dd);
-                      for (int g = 0; g < gcount; ++g) {
-                        const float hval = fmaxf(acc[g] + bias, 0.f);
-#pragma unroll
-                        for (int dst = 0; dst < kCluster; ++dst)
-                          cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = hval;
-                        a.h[(size_t)(n0 + g) * f.d + dd] = hval;
-                      }
-                    });
+    // ---- FC1: my slice of the hidden units, H = relu(Wsq z + bsq) ------------------------------
+    gemv_rows<T, GMAX>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
+                       2 * f.c, gcount, [&](int r, const float* acc) {
+                         const int dd = rank * f.dq + r;
+                         const float bias = s.bias_h[r];
+                         for (int g = 0; g < gcount; ++g) {
+                           const float hval = fmaxf(acc[g] + bias, 0.f);
+                           for (int dst = 0; dst < f.cs; ++dst)
+                             cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = hval;
+                           a.h[(size_t)(n0 + g) * f.d + dd] = hval;
+                         }
+                       });
     cluster.sync();
-    // ---- FC2: gates of my channels, both modalities -------------------------------------------
-    for (int mod = 0; mod < 2; ++mod) {
-      const float* w = mod ? a.w_s : a.w_v;
-      const float* bias_v = mod ? a.b_s : a.b_v;
-      float* gout = mod ? a.g_b : a.g_a;
-      gemv_rows<GMAX>(w, f.d, rank * f.cq, f.cq, f.d, s.vec_b, f.d, gcount, [&](int r, const float* acc) {
-        const int ch = rank * f.cq + r;
-        const float bias = __ldg(bias_v + ch);
-        for (int g = 0; g < gcount; ++g) {
-          const float gate = sigmoidf_ref(acc[g] + bias);
-          s.scale[(g * 2 + mod) * f.cq + r] = gate * a.gate_scale;
-          gout[(size_t)(n0 + g) * f.c + ch] = gate;
-        }
-      });
-    }
+    // ---- FC2: gates of my channels, both modalities (rows [0,cq) = visual, [cq,2cq) = skeleton) --
+    gemv_rows<T, GMAX>(
+        [&](int r) {
+          return r < f.cq ? a.w_v + (size_t)(rank * f.cq + r) * f.d : a.w_s + (size_t)(rank * f.cq + r - f.cq) * f.d;
+        },
+        2 * f.cq, f.d, s.vec_b, f.d, gcount, [&](int r, const float* acc) {
+          const int mod = r >= f.cq, cl = r - mod * f.cq;
+          const int ch = rank * f.cq + cl;
+          const float bias = s.bias_g[r];
+          float* gout = mod ? a.g_b : a.g_a;
+          for (int g = 0; g < gcount; ++g) {
+            const float gate = sigmoidf_ref(acc[g] + bias);
+            s.scale[(g * 2 + mod) * f.cq + cl] = gate * a.gate_scale;
+            gout[(size_t)(n0 + g) * f.c + ch] = gate;
+          }
+        });
     __syncthreads();
     // ---- pass 2: gate from shared memory, stream out; refill freed chunks with the next group --
     const int next = grp + n_clusters;
@@ -307,8 +346,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
       __syncthreads();  // chunk j fully read -> its space may be overwritten by the async proxy
       if (tid == 0 && next_gcount > 0) issue_chunks(f, s, a.a, a.b, rank, next_n0, next_gcount, j, j + 1, pol_stream);
     }
-    // chunks of the next group that lie beyond this group's valid range (only if this group was
-    // partial, which can only be the last group) need no refill.
+    // chunks beyond this group's valid range exist only if this group was partial = the last one
     if (tid == 0 && next_gcount > 0 && vchunks < f.nchunk)
       issue_chunks(f, s, a.a, a.b, rank, next_n0, next_gcount, vchunks, f.nchunk, pol_stream);
     parity ^= 1;
@@ -319,29 +357,24 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
 // =============================================================================================
 // backward
 // =============================================================================================
-template <int L, int GMAX>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
-    fused_bwd_kernel(const FusedBwdArgs a, const FusedCfg f) {
+template <int T, int L, int GMAX>
+__global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const FusedBwdArgs a, const FusedCfg f) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int cluster_id = blockIdx.x / kCluster, n_clusters = gridDim.x / kCluster;
-  const Smem s = carve(smem_raw, f, true);
+  const int cluster_id = blockIdx.x / f.cs, n_clusters = gridDim.x / f.cs;
+  const Smem s = carve(smem_raw, f);
   const int tid = threadIdx.x;
   const uint64_t pol_stream = policy_evict_first();
 
-  if (tid == 0) {
-    for (int j = 0; j < f.nchunk; ++j) mbar_init(&s.bars[j], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
+  common_prologue<T>(f, s, nullptr, nullptr, nullptr, rank);
   if (tid == 0 && cluster_id < f.n_groups) {
     const int n0 = cluster_id * f.g;
     issue_chunks(f, s, a.go_a, a.go_b, rank, n0, min(f.g, f.n - n0), 0, f.nchunk, pol_stream);
   }
   cluster.sync();
 
-  constexpr int kPlanesPerPass = kThreadsF / L;
+  constexpr int kPlanesPerPass = T / L;
   const int lane = tid % L, grp_in_pass = tid / L;
   const int hw4 = f.hw >> 2;
   const int ncol_h = f.dq;        // outputs of the dH GEMV handled by this CTA
@@ -356,7 +389,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
 
     // ---- pass 1: <grad_out (shared), input (global, streamed once)> per plane -----------------
     for (int j = 0; j < vchunks; ++j) {
-      // issue the global loads of the first planes before blocking on the barrier
       mbar_wait(&s.bars[j], parity);
       for (int pp = grp_in_pass; pp < f.pc; pp += kPlanesPerPass) {
         const int p = j * f.pc + pp;
@@ -388,45 +420,41 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
     }
     __syncthreads();
     // ---- dE of my channels -> all CTAs + global ------------------------------------------------
-    for (int p = tid; p < vplanes; p += kThreadsF) {
+    for (int p = tid; p < vplanes; p += T) {
       int g, mod, cl;
       plane_coords(f, p, g, mod, cl);
       const int ch = rank * f.cq + cl;
       const float gate = __ldg((mod ? a.g_b : a.g_a) + (size_t)(n0 + g) * f.c + ch);
       const float de = s.psum[p] * a.gate_scale * gate * (1.f - gate);
       s.scale[p] = gate * a.gate_scale;
-#pragma unroll
-      for (int dst = 0; dst < kCluster; ++dst)
+      for (int dst = 0; dst < f.cs; ++dst)
         cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + mod * f.c + ch] = de;
       (mod ? a.de_b : a.de_a)[(size_t)(n0 + g) * f.c + ch] = de;
     }
-    for (int i = tid; i < kThreadsF * GMAX; i += kThreadsF) s.part[i] = 0.f;
+    for (int i = tid; i < T * GMAX; i += T) s.part[i] = 0.f;
     cluster.sync();
-    // ---- dH for my quarter of the hidden units: dE_a Wv + dE_b Ws, masked by H > 0 -------------
-    gemv_cols_partial<GMAX>(a.w_v, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
-    gemv_cols_partial<GMAX>(a.w_s, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount, s.part);
+    // ---- dH for my slice of the hidden units: dE_a Wv + dE_b Ws, masked by H > 0 ----------------
+    gemv_cols_partial<T, GMAX>(a.w_v, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
+    gemv_cols_partial<T, GMAX>(a.w_s, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount, s.part);
     __syncthreads();
     {
-      const int slices = kThreadsF / ncol_h;
-      for (int o = tid; o < ncol_h * gcount; o += kThreadsF) {
+      const int slices = T / ncol_h;
+      for (int o = tid; o < ncol_h * gcount; o += T) {
         const int g = o / ncol_h, col = o - g * ncol_h;
         float v = 0.f;
         for (int sl = 0; sl < slices; ++sl) v += s.part[((size_t)sl * GMAX + g) * ncol_h + col];
         const int dd = rank * f.dq + col;
         const float hval = __ldg(a.h + (size_t)(n0 + g) * f.d + dd);
         v = hval > 0.f ? v : 0.f;
-#pragma unroll
-        for (int dst = 0; dst < kCluster; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = v;
+        for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = v;
         a.dh[(size_t)(n0 + g) * f.d + dd] = v;
       }
     }
-    __syncthreads();
-    for (int i = tid; i < kThreadsF * GMAX; i += kThreadsF) s.part[i] = 0.f;
     cluster.sync();
     // ---- dZ of my channels: dH Wsq[:, my columns] -----------------------------------------------
     {
       // columns of this CTA: [rank*cq, +cq) of the visual half and [C + rank*cq, +cq) of the skeleton half
-      const int slices = kThreadsF / ncol_z;
+      const int slices = T / ncol_z;
       const int col = tid % ncol_z, sl = tid / ncol_z;
       const int gcol = (col < f.cq) ? rank * f.cq + col : f.c + rank * f.cq + (col - f.cq);
       const int span = (f.d + slices - 1) / slices;
@@ -434,7 +462,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
       float acc[GMAX];
 #pragma unroll
       for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
-#pragma unroll 4
+#pragma unroll 16
       for (int kk = ka; kk < kb; ++kk) {
         const float wv = __ldg(a.w_sq + (size_t)kk * 2 * f.c + gcol);
 #pragma unroll
@@ -444,7 +472,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
 #pragma unroll
       for (int g = 0; g < GMAX; ++g) s.part[((size_t)sl * GMAX + g) * ncol_z + col] = acc[g];
       __syncthreads();
-      for (int o = tid; o < ncol_z * gcount; o += kThreadsF) {
+      for (int o = tid; o < ncol_z * gcount; o += T) {
         const int g = o / ncol_z, c2 = o - g * ncol_z;
         float v = 0.f;
         for (int s2 = 0; s2 < slices; ++s2) v += s.part[((size_t)s2 * GMAX + g) * ncol_z + c2];
@@ -485,19 +513,21 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsF, 1)
 }
 
 // ---- host side ------------------------------------------------------------------------------
-bool make_cfg(int n, int c, int hw, int d, FusedCfg* out) {
-  if (n <= 0 || c % (4 * kCluster) != 0 || d % (4 * kCluster) != 0 || hw % 4 != 0) return false;
+// cs = 4 -> one CTA per SM (~200 KB of planes), cs = 8 -> two CTAs per SM (~100 KB each)
+bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out) {
+  if (n <= 0 || c % (4 * cs) != 0 || d % (4 * cs) != 0 || hw % 4 != 0) return false;
   FusedCfg f;
-  f.n = n; f.c = c; f.hw = hw; f.d = d;
-  f.cq = c / kCluster; f.dq = d / kCluster;
+  f.n = n; f.c = c; f.hw = hw; f.d = d; f.cs = cs; f.threads = threads;
+  f.cq = c / cs; f.dq = d / cs;
   const size_t slice = (size_t)2 * f.cq * hw * sizeof(float);  // one sample, both modalities, this CTA
-  if (slice == 0 || slice > kDataBudget) return false;
-  f.g = (int)(kDataBudget / slice);
+  const size_t budget = cs == 4 ? 204800 : 102400;
+  if (slice == 0 || slice > budget) return false;
+  f.g = (int)(budget / slice);
   if (f.g > 2) f.g = 2;  // GMAX
   if (f.g > n) f.g = n;
   f.pl = f.g * 2 * f.cq;
   // transposed GEMVs map one thread per (slice, column): the column counts must divide the block
-  if (kThreadsF % f.dq != 0 || kThreadsF % (2 * f.cq) != 0 || f.dq > kThreadsF || 2 * f.cq > kThreadsF) return false;
+  if (f.dq > threads || 2 * f.cq > threads || threads % f.dq != 0 || threads % (2 * f.cq) != 0) return false;
   // chunking: equal chunks that never straddle a (sample, modality) slice and are TMA-sized
   int pc = f.cq;
   while (f.pl / pc < 8 && pc % 2 == 0 && ((size_t)(pc / 2) * hw * 4) % 16 == 0 && (size_t)(pc / 2) * hw * 4 >= 8192)
@@ -508,8 +538,20 @@ bool make_cfg(int n, int c, int hw, int d, FusedCfg* out) {
   if (((size_t)pc * hw * 4) % 16 != 0 || (size_t)pc * hw * 4 >= (1u << 20)) return false;  // mbarrier tx-count range
   f.n_groups = (n + f.g - 1) / f.g;
   f.data_bytes = (size_t)f.pl * hw * sizeof(float);
+  const size_t total = f.data_bytes + extras_bytes(f, true);
+  if (total > (cs == 4 ? 232448u : 115000u)) return false;
   *out = f;
   return true;
+}
+
+bool make_cfg(int n, int c, int hw, int d, FusedCfg* out) {
+  const int want_cs = g_fused_cluster;
+  const int thr4 = g_fused_threads ? g_fused_threads : 512;
+  const int thr8 = g_fused_threads ? g_fused_threads : 256;
+  if (want_cs == 4) return make_cfg_cs(n, c, hw, d, 4, thr4, out);
+  if (want_cs == 8) return make_cfg_cs(n, c, hw, d, 8, thr8 > 256 ? 256 : thr8, out);
+  if (make_cfg_cs(n, c, hw, d, 8, 256, out)) return true;
+  return make_cfg_cs(n, c, hw, d, 4, thr4, out);
 }
 
 int lanes_for(int hw) {
@@ -519,8 +561,68 @@ int lanes_for(int hw) {
   return l;
 }
 
-template <typename Kern>
-int launch_cluster(Kern kern, const void* args_ptr, const FusedCfg& f, bool bwd, cudaStream_t st, int tag);
+template <typename Args, typename K>
+int do_launch(K kern, const Args& args, const FusedCfg& f, bool bwd, cudaStream_t st, int tag) {
+  const size_t smem = f.data_bytes + extras_bytes(f, bwd);
+  GML_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(f.threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = f.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  // persistent grid: as many clusters as can be co-resident, capped by the work
+  cfg.gridDim = dim3(kNumSMs * 2 / f.cs * f.cs);
+  static std::mutex mu;
+  static std::map<std::pair<const void*, size_t>, int> cache;
+  int max_clusters = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair((const void*)kern, smem * 16 + (size_t)f.cs);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      max_clusters = it->second;
+    } else {
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) {
+        cudaGetLastError();
+        max_clusters = f.cs == 4 ? 33 : 28;  // conservative fallbacks
+      }
+      cache[key] = max_clusters;
+    }
+  }
+  int clusters = f.n_groups < max_clusters ? f.n_groups : max_clusters;
+  if (clusters < 1) clusters = 1;
+  cfg.gridDim = dim3(clusters * f.cs);
+  {
+    LaunchScope ls(tag, st);
+    GML_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args, f));
+  }
+  GML_LAUNCH_CHECK();
+  return GML_OK;
+}
+
+template <int T, typename Args>
+int dispatch_fwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
+  const int l = lanes_for(f.hw);
+#define GML_FWD(LL, GG) return do_launch(fused_fwd_kernel<T, LL, GG>, args, f, false, st, kTagFusedFwd)
+  if (f.g == 1) { if (l == 32) GML_FWD(32, 1); if (l == 16) GML_FWD(16, 1); GML_FWD(8, 1); }
+  if (l == 32) GML_FWD(32, 2);
+  if (l == 16) GML_FWD(16, 2);
+  GML_FWD(8, 2);
+#undef GML_FWD
+}
+template <int T, typename Args>
+int dispatch_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
+  const int l = lanes_for(f.hw);
+#define GML_BWD(LL, GG) return do_launch(fused_bwd_kernel<T, LL, GG>, args, f, true, st, kTagFusedBwd)
+  if (f.g == 1) { if (l == 32) GML_BWD(32, 1); if (l == 16) GML_BWD(16, 1); GML_BWD(8, 1); }
+  if (l == 32) GML_BWD(32, 2);
+  if (l == 16) GML_BWD(16, 2);
+  GML_BWD(8, 2);
+#undef GML_BWD
+}
 
 }  // namespace
 
@@ -533,45 +635,8 @@ bool fused_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mod
   // small next to the group's feature-map bytes (MMTM4's 512x7^2 goes the streaming way)
   const double w_bytes = 4.0 * (2.0 * c_v * d + 2.0 * c_v * d);
   const double group_bytes = 2.0 * f.g * 2.0 * c_v * hw_v * 4.0;
-  if (w_bytes > 1.0 * group_bytes) return false;
-  return true;
+  return w_bytes <= group_bytes;
 }
-
-namespace {
-template <typename Args, typename K>
-int do_launch(K kern, const Args& args, const FusedCfg& f, bool bwd, cudaStream_t st, int tag) {
-  const size_t smem = smem_bytes(f, bwd);
-  if (smem > 232448) return GML_E_UNSUPPORTED;
-  GML_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // persistent grid: as many clusters as can be co-resident (1 CTA per SM), capped by the work
-  static int max_clusters_cache[2] = {0, 0};
-  int& max_clusters = max_clusters_cache[bwd ? 1 : 0];
-  if (max_clusters == 0) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kNumSMs / kCluster * kCluster);
-    cfg.blockDim = dim3(kThreadsF);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc <= 0) {
-      cudaGetLastError();
-      nc = kNumSMs / kCluster - 4;  // conservative: 33 clusters of 4 fit a B200 (SURVEY / microarch notes)
-    }
-    max_clusters = nc;
-  }
-  int clusters = f.n_groups < max_clusters ? f.n_groups : max_clusters;
-  if (clusters < 1) clusters = 1;
-  {
-    LaunchScope ls(tag, st);
-    kern<<<clusters * kCluster, kThreadsF, smem, st>>>(args, f);
-  }
-  GML_LAUNCH_CHECK();
-  return GML_OK;
-}
-}  // namespace
 
 int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st) {
   FusedCfg f;
@@ -579,15 +644,7 @@ int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st) {
   if (!aligned16(args.a) || !aligned16(args.b) || !aligned16(args.a_out) || !aligned16(args.b_out) ||
       !aligned16(args.w_sq) || !aligned16(args.w_v) || !aligned16(args.w_s))
     return GML_E_UNSUPPORTED;
-  const int l = lanes_for(f.hw);
-  if (f.g == 1) {
-    if (l == 32) return do_launch(fused_fwd_kernel<32, 1>, args, f, false, st, kTagFusedFwd);
-    if (l == 16) return do_launch(fused_fwd_kernel<16, 1>, args, f, false, st, kTagFusedFwd);
-    return do_launch(fused_fwd_kernel<8, 1>, args, f, false, st, kTagFusedFwd);
-  }
-  if (l == 32) return do_launch(fused_fwd_kernel<32, 2>, args, f, false, st, kTagFusedFwd);
-  if (l == 16) return do_launch(fused_fwd_kernel<16, 2>, args, f, false, st, kTagFusedFwd);
-  return do_launch(fused_fwd_kernel<8, 2>, args, f, false, st, kTagFusedFwd);
+  return f.threads == 512 ? dispatch_fwd<512>(args, f, st) : dispatch_fwd<256>(args, f, st);
 }
 
 int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st) {
@@ -596,15 +653,7 @@ int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st) {
   if (!aligned16(args.go_a) || !aligned16(args.go_b) || !aligned16(args.a) || !aligned16(args.b) ||
       !aligned16(args.d_a) || !aligned16(args.d_b))
     return GML_E_UNSUPPORTED;
-  const int l = lanes_for(f.hw);
-  if (f.g == 1) {
-    if (l == 32) return do_launch(fused_bwd_kernel<32, 1>, args, f, true, st, kTagFusedBwd);
-    if (l == 16) return do_launch(fused_bwd_kernel<16, 1>, args, f, true, st, kTagFusedBwd);
-    return do_launch(fused_bwd_kernel<8, 1>, args, f, true, st, kTagFusedBwd);
-  }
-  if (l == 32) return do_launch(fused_bwd_kernel<32, 2>, args, f, true, st, kTagFusedBwd);
-  if (l == 16) return do_launch(fused_bwd_kernel<16, 2>, args, f, true, st, kTagFusedBwd);
-  return do_launch(fused_bwd_kernel<8, 2>, args, f, true, st, kTagFusedBwd);
+  return f.threads == 512 ? dispatch_bwd<512>(args, f, st) : dispatch_bwd<256>(args, f, st);
 }
 
 }  // namespace gml

@@ -85,6 +85,11 @@ const char* gml_kernel_tag_name(int tag);
 void gml_profile_enable(int on);
 void gml_profile_reset(void);
 int gml_profile_read(int tag, double* total_ms, int64_t* launches);
+/* Process-wide tuning knobs for measurement sweeps (defaults are what ships):
+ *   "l2_chunk_mb"    bytes of feature map the streaming path pushes through both passes at once
+ *   "fused_cluster"  0 auto | 4 (one CTA per SM) | 8 (two CTAs per SM)
+ *   "fused_threads"  0 auto | 256 | 512                                                      */
+int gml_set_tunable(const char* name, int64_t value);
 
 /* ---------------------------------------------------------------------------------------
  * MMTM forward.  Replaces MMTM_mitigate.forward, src/balanced_mmtm.py:49-154.

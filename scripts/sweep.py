@@ -1,0 +1,105 @@
+#!/usr/bin/env python3
+"""Kernel-path sweep on one B200: forward and backward of one MMTM block timed separately
+through the C ABI (CUDA events around each call, L2 flushed between iterations), for every
+shape x batch x kernel-path variant.  Writes gpurun_out/sweep.json and prints a table.
+
+    python scripts/sweep.py [--batches 32,256,1024] [--iters 12] [--variants ...]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from bench import SHAPES, BlockBuffers, measured_peak  # noqa: E402
+from greedy_multimodal_learning_b200 import _lib as L  # noqa: E402
+
+VARIANTS = {
+    # name: (flags, tunables)
+    "stream_c40": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 40}),
+    "stream_c16": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 16}),
+    "stream_c80": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 80}),
+    "stream_nochunk": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 100000}),
+    "fused_cs4_t512": (L.F_FORCE_FUSED, {"fused_cluster": 4, "fused_threads": 512}),
+    "fused_cs4_t256": (L.F_FORCE_FUSED, {"fused_cluster": 4, "fused_threads": 256}),
+    "fused_cs8_t256": (L.F_FORCE_FUSED, {"fused_cluster": 8, "fused_threads": 256}),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batches", default="32,256,1024")
+    ap.add_argument("--iters", type=int, default=12)
+    ap.add_argument("--variants", default=",".join(VARIANTS))
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
+    args = ap.parse_args()
+    lib = L.load()
+    dev = torch.device("cuda:0")
+    peak, _ = measured_peak()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    rows = []
+    for c, h in SHAPES:
+        for n in [int(x) for x in args.batches.split(",")]:
+            b = BlockBuffers(torch, L, n, c, h, dev, seed=c)
+            u = n * c * h * h * 4
+            P = lambda t: t.data_ptr()
+            w, dw = b.w, b.dw
+
+            def fwd(flags):
+                return lib.gml_mmtm_fwd(P(b.a), P(b.b), P(b.a_out), P(b.b_out), P(w[0]), P(w[1]), P(w[2]), P(w[3]),
+                                        P(w[4]), P(w[5]), P(b.z), P(b.hid), P(b.g_a), P(b.g_b), P(b.gate_sum),
+                                        P(b.run_v), P(b.run_s), 0, None, None, None, 0, b.dims, 0, 1.0, flags,
+                                        stream.cuda_stream)
+
+            def bwd(flags):
+                return lib.gml_mmtm_bwd(P(b.go_a), P(b.go_b), P(b.a), P(b.b), P(w[0]), P(w[2]), P(w[4]), P(b.z),
+                                        P(b.hid), P(b.g_a), P(b.g_b), None, None, None, None, P(b.d_a), P(b.d_b),
+                                        P(dw[0]), P(dw[1]), P(dw[2]), P(dw[3]), P(dw[4]), P(dw[5]), P(b.ws),
+                                        b.ws_bytes, b.dims, 0, 1.0, flags, stream.cuda_stream)
+
+            for name in args.variants.split(","):
+                flags, tun = VARIANTS[name]
+                for k, v in {"l2_chunk_mb": 40, "fused_cluster": 0, "fused_threads": 0, **tun}.items():
+                    L.check(lib.gml_set_tunable(k.encode(), v))
+                rc = fwd(flags)
+                if rc == -5:
+                    continue  # unsupported shape for this variant
+                L.check(rc, "fwd")
+                L.check(bwd(flags), "bwd")
+                torch.cuda.synchronize()
+                res = {}
+                for what, fn, units in (("fwd", fwd, 4), ("bwd", bwd, 6)):
+                    ts = []
+                    for _ in range(args.iters + 2):
+                        flush.zero_()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        L.check(fn(flags), what)
+                        e1.record()
+                        e1.synchronize()
+                        ts.append(e0.elapsed_time(e1))
+                    ts = sorted(ts[2:])
+                    med = ts[len(ts) // 2]
+                    res[what] = {"ms": med, "gbs": units * u / (med * 1e-3) / 1e9, "min_ms": ts[0]}
+                tot = res["fwd"]["ms"] + res["bwd"]["ms"]
+                row = {"c": c, "h": h, "n": n, "variant": name, "fwd_ms": res["fwd"]["ms"], "bwd_ms": res["bwd"]["ms"],
+                       "fwd_gbs": res["fwd"]["gbs"], "bwd_gbs": res["bwd"]["gbs"],
+                       "fwd_bwd_gbs": 10 * u / (tot * 1e-3) / 1e9, "frac_peak": 10 * u / (tot * 1e-3) / 1e9 / peak}
+                rows.append(row)
+                print("C=%3d H=%2d N=%4d %-16s fwd %8.3f ms %6.0f GB/s | bwd %8.3f ms %6.0f GB/s | fwd+bwd %6.0f GB/s "
+                      "= %4.1f%% of %.0f" % (c, h, n, name, row["fwd_ms"], row["fwd_gbs"], row["bwd_ms"],
+                                             row["bwd_gbs"], row["fwd_bwd_gbs"], 100 * row["frac_peak"], peak),
+                      flush=True)
+            del b
+            torch.cuda.empty_cache()
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump(rows, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -107,7 +107,9 @@ def test_learning_speed_on_the_real_model_matches_oracle():
     for _ in range(3):
         d = cb.compute_BDR()
         d_ref = ls.update(want)
-        assert abs(d - d_ref) <= 1e-6 * max(abs(d_ref), 1e-3)
+        # d_BDR is a difference of log10 ratios: a 1e-6 relative error of the bucket sums moves each
+        # log10 by 1e-6 / ln(10), i.e. an ABSOLUTE 4 * 4.3e-7 in the worst case
+        assert abs(d - d_ref) <= 2e-6
     # gradients re-allocated (zero_grad(set_to_none=True)) -> table is rebuilt transparently
     for p in model.parameters():
         p.grad = None
