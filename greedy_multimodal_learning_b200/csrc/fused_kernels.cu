@@ -101,10 +101,11 @@ struct Smem {
   float* vec_a;   // [g][2C]  z (fwd) / dE (bwd), full vector, filled by all CTAs of the cluster
   float* vec_b;   // [g][D]   h (fwd) / dH (bwd)
   float* part;    // cross-warp partial sums of the transposed GEMVs (backward)
+  int* done;      // [nchunk] planes of chunk j already drained in the output pass
 };
 
 __host__ __device__ inline size_t extras_bytes(const FusedCfg& f, bool bwd) {
-  size_t b = kMaxChunks * sizeof(uint64_t) + 3 * (size_t)f.pl * 4 + ((size_t)f.dq + 2 * f.cq) * 4 +
+  size_t b = kMaxChunks * (sizeof(uint64_t) + sizeof(int)) + 3 * (size_t)f.pl * 4 + ((size_t)f.dq + 2 * f.cq) * 4 +
              (size_t)f.g * 2 * f.c * 4 + (size_t)f.g * f.d * 4;
   if (bwd) b += (size_t)f.threads * f.g * 4;  // part[slices][g][cols], slices * cols == threads
   return b + 16;
@@ -115,6 +116,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const FusedCfg& f) {
   s.data = reinterpret_cast<float*>(base);
   unsigned char* p = base + f.data_bytes;
   s.bars = reinterpret_cast<uint64_t*>(p); p += kMaxChunks * sizeof(uint64_t);
+  s.done = reinterpret_cast<int*>(p); p += kMaxChunks * sizeof(int);
   s.vec_a = reinterpret_cast<float*>(p); p += (size_t)f.g * 2 * f.c * sizeof(float);   // 16-byte aligned
   s.vec_b = reinterpret_cast<float*>(p); p += (size_t)f.g * f.d * sizeof(float);       // 16-byte aligned
   s.psum = reinterpret_cast<float*>(p); p += f.pl * sizeof(float);
@@ -149,13 +151,29 @@ __device__ __forceinline__ void issue_chunks(const FusedCfg& f, const Smem& s, c
   }
 }
 
+
+// Output-pass bookkeeping: the group that drains the LAST plane of chunk j re-arms the chunk with
+// the next group's data (no block-wide barrier in the streaming loops).
+__device__ __forceinline__ void plane_drained(const FusedCfg& f, const Smem& s, int p, const float* xa, const float* xb,
+                                              int rank, int next_n0, int next_gcount, uint64_t policy) {
+  const int j = p / f.pc;
+  __threadfence_block();  // this group's shared-memory reads are done before the count is published
+  const int prev = atomicAdd(&s.done[j], 1);
+  if (prev == f.pc - 1) {
+    s.done[j] = 0;
+    if (next_gcount > 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue_chunks(f, s, xa, xb, rank, next_n0, next_gcount, j, j + 1, policy);
+    }
+  }
+}
+
 // y[row] = <W[row0 + row, 0:K], x[g, 0:K]>, K % 4 == 0.  Each warp owns kRowsPerBatch rows at a time
 // and issues all their weight loads before the first FMA (the weights come from L2: the cost is
 // latency, so several rows must be in flight); lane r then finishes row r.
-template <int T, int GMAX, typename RowPtr, typename Epi>
-__device__ __forceinline__ void gemv_rows(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
-                                          Epi epi) {
-  constexpr int R = kRowsPerBatch;
+template <int T, int GMAX, int R, typename RowPtr, typename Epi>
+__device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
+                                            Epi epi) {
   constexpr int kWarps = T / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k4 = k >> 2;
@@ -195,6 +213,15 @@ __device__ __forceinline__ void gemv_rows(RowPtr rowptr, int nrows, int k, const
   }
 }
 
+template <int T, int GMAX, typename RowPtr, typename Epi>
+__device__ __forceinline__ void gemv_rows(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
+                                          Epi epi) {
+  // few rows: spread them over more warps (one L2 round trip either way)
+  if (nrows <= (T / 32)) gemv_rows_r<T, GMAX, 1>(rowptr, nrows, k, x, ldx, gcount, epi);
+  else if (nrows <= 2 * (T / 32)) gemv_rows_r<T, GMAX, 2>(rowptr, nrows, k, x, ldx, gcount, epi);
+  else gemv_rows_r<T, GMAX, kRowsPerBatch>(rowptr, nrows, k, x, ldx, gcount, epi);
+}
+
 // y[col] = sum_k x[g, k] * W[k, col0 + col] (transposed GEMV): thread = (k-slice, col), coalesced in
 // col.  Partials are ADDED into s_part[slice][g][col]; the caller reduces the slices in a fixed order.
 template <int T, int GMAX>
@@ -224,7 +251,10 @@ __device__ __forceinline__ void common_prologue(const FusedCfg& f, const Smem& s
                                                 const float* b_s, int rank) {
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int j = 0; j < f.nchunk; ++j) mbar_init(&s.bars[j], 1);
+    for (int j = 0; j < f.nchunk; ++j) {
+      mbar_init(&s.bars[j], 1);
+      s.done[j] = 0;
+    }
     fence_mbar_init();
   }
   if (b_sq) {
@@ -267,20 +297,18 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const 
     const int vchunks = vplanes / f.pc;
 
     // ---- pass 1: plane sums straight out of shared memory as chunks land --------------------
-    for (int j = 0; j < vchunks; ++j) {
-      mbar_wait(&s.bars[j], parity);
-      for (int pp = grp_in_pass; pp < f.pc; pp += kPlanesPerPass) {
-        const int p = j * f.pc + pp;
-        const float4* v = reinterpret_cast<const float4*>(s.data + (size_t)p * f.hw);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-        for (int i = lane; i < hw4; i += L) {
-          const float4 x = v[i];
-          a0 += x.x; a1 += x.y; a2 += x.z; a3 += x.w;
-        }
-        const float t = group_sum<L>((a0 + a1) + (a2 + a3));
-        if (lane == 0) s.psum[p] = t;
+    // group gi owns planes gi, gi + NG, ...: every warp has work in every chunk wave
+    for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
+      mbar_wait(&s.bars[p / f.pc], parity);
+      const float4* v = reinterpret_cast<const float4*>(s.data + (size_t)p * f.hw);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+      for (int i = lane; i < hw4; i += L) {
+        const float4 x = v[i];
+        a0 += x.x; a1 += x.y; a2 += x.z; a3 += x.w;
       }
+      const float t = group_sum<L>((a0 + a1) + (a2 + a3));
+      if (lane == 0) s.psum[p] = t;
     }
     __syncthreads();
     // ---- squeeze vector -> every CTA of the cluster (DSMEM) + global z ------------------------
@@ -327,28 +355,24 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const 
     const int next = grp + n_clusters;
     const int next_n0 = next * f.g;
     const int next_gcount = next < f.n_groups ? min(f.g, f.n - next_n0) : 0;
-    for (int j = 0; j < vchunks; ++j) {
-      for (int pp = grp_in_pass; pp < f.pc; pp += kPlanesPerPass) {
-        const int p = j * f.pc + pp;
-        int g, mod, cl;
-        plane_coords(f, p, g, mod, cl);
-        const float sc = s.scale[p];
-        const float4* v = reinterpret_cast<const float4*>(s.data + (size_t)p * f.hw);
-        float4* o = reinterpret_cast<float4*>((mod ? a.b_out : a.a_out) +
-                                              ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw);
-#pragma unroll 4
-        for (int i = lane; i < hw4; i += L) {
-          float4 x = v[i];
-          x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
-          stg_stream(o + i, x);
-        }
+    for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      const float sc = s.scale[p];
+      const float4* v = reinterpret_cast<const float4*>(s.data + (size_t)p * f.hw);
+      float4* o = reinterpret_cast<float4*>((mod ? a.b_out : a.a_out) +
+                                            ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw);
+#pragma unroll 8
+      for (int i = lane; i < hw4; i += L) {
+        float4 x = v[i];
+        x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
+        stg_stream(o + i, x);
       }
-      __syncthreads();  // chunk j fully read -> its space may be overwritten by the async proxy
-      if (tid == 0 && next_gcount > 0) issue_chunks(f, s, a.a, a.b, rank, next_n0, next_gcount, j, j + 1, pol_stream);
+      if (L < 32) __syncwarp();
+      if (lane == 0) plane_drained(f, s, p, a.a, a.b, rank, next_n0, next_gcount, pol_stream);
     }
     // chunks beyond this group's valid range exist only if this group was partial = the last one
-    if (tid == 0 && next_gcount > 0 && vchunks < f.nchunk)
-      issue_chunks(f, s, a.a, a.b, rank, next_n0, next_gcount, vchunks, f.nchunk, pol_stream);
+    __syncthreads();  // all refills of this iteration are issued; psum/scale may be reused
     parity ^= 1;
   }
   cluster.sync();  // nobody exits while a sibling may still address its shared memory
@@ -387,44 +411,60 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
     const int vplanes = gcount * 2 * f.cq;
     const int vchunks = vplanes / f.pc;
 
+    // ---- early, latency-hiding loads of the per-plane gate and my slice of the ReLU mask -------
+    float gate_pf = 0.f, h_pf = 0.f;
+    if (tid < vplanes) {
+      int g, mod, cl;
+      plane_coords(f, tid, g, mod, cl);
+      gate_pf = __ldg((mod ? a.g_b : a.g_a) + (size_t)(n0 + g) * f.c + rank * f.cq + cl);
+    }
+    if (tid < ncol_h * gcount) {
+      const int g = tid / ncol_h, col = tid - g * ncol_h;
+      h_pf = __ldg(a.h + (size_t)(n0 + g) * f.d + rank * f.dq + col);
+    }
     // ---- pass 1: <grad_out (shared), input (global, streamed once)> per plane -----------------
-    for (int j = 0; j < vchunks; ++j) {
-      mbar_wait(&s.bars[j], parity);
-      for (int pp = grp_in_pass; pp < f.pc; pp += kPlanesPerPass) {
-        const int p = j * f.pc + pp;
-        int g, mod, cl;
-        plane_coords(f, p, g, mod, cl);
-        const float4* gv = reinterpret_cast<const float4*>(s.data + (size_t)p * f.hw);
-        const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) +
-                                                           ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int i = lane;
-        for (; i + 3 * L < hw4; i += 4 * L) {
-          float4 x[4];
+    for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      const float4* gv = reinterpret_cast<const float4*>(s.data + (size_t)p * f.hw);
+      const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) +
+                                                         ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      bool waited = false;
+      for (int i0 = 0; i0 < hw4; i0 += 8 * L) {
+        // up to 8 independent 128-bit global loads per lane in flight, issued BEFORE blocking on the
+        // chunk barrier so their latency overlaps the wait
+        float4 x[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) x[u] = ldg_hint(xv + i + u * L, pol_stream);
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + lane + u * L;
+          x[u] = i < hw4 ? ldg_hint(xv + i, pol_stream) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (!waited) {
+          mbar_wait(&s.bars[p / f.pc], parity);
+          waited = true;
+        }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 gg = gv[i + u * L];
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + lane + u * L;
+          if (i < hw4) {
+            const float4 gg = gv[i];
             a0 = fmaf(gg.x, x[u].x, a0); a1 = fmaf(gg.y, x[u].y, a1);
             a2 = fmaf(gg.z, x[u].z, a2); a3 = fmaf(gg.w, x[u].w, a3);
           }
         }
-        for (; i < hw4; i += L) {
-          const float4 x = ldg_hint(xv + i, pol_stream), gg = gv[i];
-          a0 = fmaf(gg.x, x.x, a0); a1 = fmaf(gg.y, x.y, a1); a2 = fmaf(gg.z, x.z, a2); a3 = fmaf(gg.w, x.w, a3);
-        }
-        const float t = group_sum<L>((a0 + a1) + (a2 + a3));
-        if (lane == 0) s.psum[p] = t;
       }
+      const float t = group_sum<L>((a0 + a1) + (a2 + a3));
+      if (lane == 0) s.psum[p] = t;
     }
     __syncthreads();
     // ---- dE of my channels -> all CTAs + global ------------------------------------------------
-    for (int p = tid; p < vplanes; p += T) {
+    if (tid < vplanes) {
+      const int p = tid;
       int g, mod, cl;
       plane_coords(f, p, g, mod, cl);
       const int ch = rank * f.cq + cl;
-      const float gate = __ldg((mod ? a.g_b : a.g_a) + (size_t)(n0 + g) * f.c + ch);
+      const float gate = gate_pf;
       const float de = s.psum[p] * a.gate_scale * gate * (1.f - gate);
       s.scale[p] = gate * a.gate_scale;
       for (int dst = 0; dst < f.cs; ++dst)
@@ -439,13 +479,12 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
     __syncthreads();
     {
       const int slices = T / ncol_h;
-      for (int o = tid; o < ncol_h * gcount; o += T) {
-        const int g = o / ncol_h, col = o - g * ncol_h;
+      if (tid < ncol_h * gcount) {
+        const int g = tid / ncol_h, col = tid - g * ncol_h;
         float v = 0.f;
         for (int sl = 0; sl < slices; ++sl) v += s.part[((size_t)sl * GMAX + g) * ncol_h + col];
         const int dd = rank * f.dq + col;
-        const float hval = __ldg(a.h + (size_t)(n0 + g) * f.d + dd);
-        v = hval > 0.f ? v : 0.f;
+        v = h_pf > 0.f ? v : 0.f;
         for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = v;
         a.dh[(size_t)(n0 + g) * f.d + dd] = v;
       }
@@ -485,28 +524,23 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
     const int next = grp + n_clusters;
     const int next_n0 = next * f.g;
     const int next_gcount = next < f.n_groups ? min(f.g, f.n - next_n0) : 0;
-    for (int j = 0; j < vchunks; ++j) {
-      for (int pp = grp_in_pass; pp < f.pc; pp += kPlanesPerPass) {
-        const int p = j * f.pc + pp;
-        int g, mod, cl;
-        plane_coords(f, p, g, mod, cl);
-        const float sc = s.scale[p], ad = s.addv[p];
-        const float4* v = reinterpret_cast<const float4*>(s.data + (size_t)p * f.hw);
-        float4* o = reinterpret_cast<float4*>((mod ? a.d_b : a.d_a) +
-                                              ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw);
-#pragma unroll 4
-        for (int i = lane; i < hw4; i += L) {
-          float4 x = v[i];
-          x.x = fmaf(x.x, sc, ad); x.y = fmaf(x.y, sc, ad); x.z = fmaf(x.z, sc, ad); x.w = fmaf(x.w, sc, ad);
-          stg_stream(o + i, x);
-        }
+    for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      const float sc = s.scale[p], ad = s.addv[p];
+      const float4* v = reinterpret_cast<const float4*>(s.data + (size_t)p * f.hw);
+      float4* o = reinterpret_cast<float4*>((mod ? a.d_b : a.d_a) +
+                                            ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw);
+#pragma unroll 8
+      for (int i = lane; i < hw4; i += L) {
+        float4 x = v[i];
+        x.x = fmaf(x.x, sc, ad); x.y = fmaf(x.y, sc, ad); x.z = fmaf(x.z, sc, ad); x.w = fmaf(x.w, sc, ad);
+        stg_stream(o + i, x);
       }
-      __syncthreads();
-      if (tid == 0 && next_gcount > 0)
-        issue_chunks(f, s, a.go_a, a.go_b, rank, next_n0, next_gcount, j, j + 1, pol_stream);
+      if (L < 32) __syncwarp();
+      if (lane == 0) plane_drained(f, s, p, a.go_a, a.go_b, rank, next_n0, next_gcount, pol_stream);
     }
-    if (tid == 0 && next_gcount > 0 && vchunks < f.nchunk)
-      issue_chunks(f, s, a.go_a, a.go_b, rank, next_n0, next_gcount, vchunks, f.nchunk, pol_stream);
+    __syncthreads();
     parity ^= 1;
   }
   cluster.sync();
@@ -526,6 +560,7 @@ bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out
   if (f.g > 2) f.g = 2;  // GMAX
   if (f.g > n) f.g = n;
   f.pl = f.g * 2 * f.cq;
+  if (f.pl > threads || f.dq * f.g > threads) return false;  // one thread per plane / hidden unit in the small steps
   // transposed GEMVs map one thread per (slice, column): the column counts must divide the block
   if (f.dq > threads || 2 * f.cq > threads || threads % f.dq != 0 || threads % (2 * f.cq) != 0) return false;
   // chunking: equal chunks that never straddle a (sample, modality) slice and are TMA-sized

@@ -134,7 +134,8 @@ def test_accuracy_counts_bit_exact():
         t0, t1, ty = torch.from_numpy(l0), torch.from_numpy(l1), torch.from_numpy(y)
         counts = torch.empty(3, dtype=torch.int32, device=DEV)
         lib = _lib.load()
-        _lib.check(lib.gml_accuracy_counts(t0.to(DEV).data_ptr(), t1.to(DEV).data_ptr(), ty.to(DEV).data_ptr(), n, k,
+        d0, d1, dy = t0.to(DEV), t1.to(DEV), ty.to(DEV)  # keep the device copies alive across the call
+        _lib.check(lib.gml_accuracy_counts(d0.data_ptr(), d1.data_ptr(), dy.data_ptr(), n, k,
                                            counts.data_ptr(), _lib.current_stream(torch.device(DEV))))
         want = [so.correct_count((t0 + t1) / 2, ty)[0], so.correct_count(t0, ty)[0], so.correct_count(t1, ty)[0]]
         assert counts.tolist() == want, (n, k)
