@@ -125,14 +125,16 @@ class BlockBuffers:
         lib = lib_mod.load()
         self.ws_bytes = lib.gml_mmtm_bwd_workspace_bytes(self.dims)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.fws_bytes = lib.gml_mmtm_fwd_workspace_bytes(self.dims)
+        self.fws = torch.empty(self.fws_bytes, dtype=torch.uint8, device=dev)
 
     def fwd_bwd(self, lib, lib_mod, stream, flags=0):
         P = lambda t: t.data_ptr()
         w = self.w
         lib_mod.check(lib.gml_mmtm_fwd(P(self.a), P(self.b), P(self.a_out), P(self.b_out), P(w[0]), P(w[1]), P(w[2]),
                                        P(w[3]), P(w[4]), P(w[5]), P(self.z), P(self.hid), P(self.g_a), P(self.g_b),
-                                       P(self.gate_sum), P(self.run_v), P(self.run_s), 0, None, None, None, 0,
-                                       self.dims, 0, 1.0, flags, stream), "gml_mmtm_fwd")
+                                       P(self.gate_sum), P(self.run_v), P(self.run_s), 0, None, None, P(self.fws),
+                                       self.fws_bytes, self.dims, 0, 1.0, flags, stream), "gml_mmtm_fwd")
         dw = self.dw
         lib_mod.check(lib.gml_mmtm_bwd(P(self.go_a), P(self.go_b), P(self.a), P(self.b), P(w[0]), P(w[2]), P(w[4]),
                                        P(self.z), P(self.hid), P(self.g_a), P(self.g_b), None, None, None, None,

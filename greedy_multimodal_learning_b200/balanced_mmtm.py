@@ -64,13 +64,15 @@ class _MMTMFunction(torch.autograd.Function):
         gate_sum = torch.empty((c_v + 1,), **f32)  # [sum_n g_a | n] so one all-reduce carries both
         st = _lib.current_stream(dev)
         P = _lib.ptr
+        ws_bytes = lib.gml_mmtm_fwd_workspace_bytes(dims)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         curate = mode in (MODE_CURATE_VISUAL, MODE_CURATE_SKELETON)
         world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
         with torch.cuda.device(dev):
             if world == 1:
                 _lib.check(lib.gml_mmtm_fwd(P(a), P(b), P(a_out), P(b_out), P(w_sq), P(b_sq), P(w_v), P(b_v), P(w_s),
                                             P(b_s), P(z), P(h), P(g_a), P(g_b), P(gate_sum), P(run_v), P(run_s), step,
-                                            P(m_a), P(m_b), None, 0, dims, mode, gate_scale, flags, st),
+                                            P(m_a), P(m_b), P(ws), ws_bytes, dims, mode, gate_scale, flags, st),
                            "gml_mmtm_fwd")
             else:
                 # data parallel: the running mean is over the GLOBAL batch (one tiny all-reduce of
@@ -79,12 +81,12 @@ class _MMTMFunction(torch.autograd.Function):
                 gate_sum[c_v] = float(n)
                 if curate:
                     _lib.check(lib.gml_mmtm_gates(P(a), P(b), P(w_sq), P(b_sq), P(w_v), P(b_v), P(w_s), P(b_s), P(z),
-                                                  P(h), P(g_a), P(g_b), P(gate_sum), P(m_a), P(m_b), None, 0, dims,
-                                                  mode, st), "gml_mmtm_gates")
+                                                  P(h), P(g_a), P(g_b), P(gate_sum), P(m_a), P(m_b), P(ws), ws_bytes,
+                                                  dims, mode, st), "gml_mmtm_gates")
                 else:
                     _lib.check(lib.gml_mmtm_fwd(P(a), P(b), P(a_out), P(b_out), P(w_sq), P(b_sq), P(w_v), P(b_v),
                                                 P(w_s), P(b_s), P(z), P(h), P(g_a), P(g_b), P(gate_sum), P(run_v),
-                                                P(run_s), step, P(m_a), P(m_b), None, 0, dims, mode, gate_scale,
+                                                P(run_s), step, P(m_a), P(m_b), P(ws), ws_bytes, dims, mode, gate_scale,
                                                 flags | _lib.F_NO_RUNNING_UPDATE, st), "gml_mmtm_fwd")
                 torch.distributed.all_reduce(gate_sum, group=dist_group)
                 # keep the count on device: divide by it inside a tiny torch op instead of syncing

@@ -96,7 +96,7 @@ size_t l2_budget_bytes() {
   long mb = g_l2_chunk_mb.load();
   if (mb < 0) {
     const char* e = getenv("GML_L2_CHUNK_MB");
-    mb = e ? atol(e) : 40;
+    mb = e ? atol(e) : (1L << 20);  // default: no chunking (measured: per-chunk launches cost more than L2 reuse gains)
     if (mb < 1) mb = 1;
     g_l2_chunk_mb.store(mb);
   }
@@ -115,7 +115,8 @@ bool live_b(int mode) { return mode != GML_MODE_CURATE_SKELETON; }
 // squeeze + excitation for samples [n0, n0 + cn)
 int gates_chunk(const float* a, const float* b, const float* w_sq, const float* b_sq, const float* w_v,
                 const float* b_v, const float* w_s, const float* b_s, float* z, float* h, float* g_a, float* g_b,
-                const float* m_a, const float* m_b, const Dims& d, int mode, int n0, int cn, bool keep, cudaStream_t st) {
+                const float* m_a, const float* m_b, const Dims& d, int mode, int n0, int cn, bool keep, cudaStream_t st,
+                void* gws, size_t gws_bytes) {
   const bool x3 = mode == GML_MODE_XMODAL_OFF;
   float* z_a = z + (size_t)n0 * d.ldz;                               // rows that receive s_a
   float* z_b = z + (size_t)(d.hoff + n0) * d.ldz;                    // rows that receive s_b
@@ -136,12 +137,12 @@ int gates_chunk(const float* a, const float* b, const float* w_sq, const float* 
     g1[1].c = h + (size_t)(d.hoff + n0) * d.d;
     cnt1 = 2;
   }
-  GML_TRY(launch_gemm(g1, cnt1, st));
+  GML_TRY(launch_gemm(g1, cnt1, st, gws, gws_bytes));
   // gates
   GemmDesc g2[2];
   g2[0] = GemmDesc{h + (size_t)n0 * d.d, w_v, g_a + (size_t)n0 * d.c_v, b_v, nullptr, cn, d.c_v, d.d, d.d, d.d, d.c_v, 0, 1, 1, kActSigmoid, 0};
   g2[1] = GemmDesc{h + (size_t)(d.hoff + n0) * d.d, w_s, g_b + (size_t)n0 * d.c_s, b_s, nullptr, cn, d.c_s, d.d, d.d, d.d, d.c_s, 0, 1, 1, kActSigmoid, 0};
-  GML_TRY(launch_gemm(g2, 2, st));
+  GML_TRY(launch_gemm(g2, 2, st, gws, gws_bytes));
   return GML_OK;
 }
 
@@ -216,6 +217,7 @@ extern "C" int gml_profile_read(int tag, double* total_ms, int64_t* launches) {
 namespace gml {
 extern int g_fused_cluster;
 extern int g_fused_threads;
+extern long long* g_fused_trace;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -224,6 +226,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
     if (value != 0 && value != 4 && value != 8) return GML_E_BADARG;
     g_fused_cluster = (int)value; return GML_OK;
   }
+  if (!strcmp(name, "fused_trace_ptr")) { g_fused_trace = reinterpret_cast<long long*>(value); return GML_OK; }
   if (!strcmp(name, "fused_threads")) {
     if (value != 0 && value != 256 && value != 512) return GML_E_BADARG;
     g_fused_threads = (int)value; return GML_OK;
@@ -240,21 +243,21 @@ extern "C" int gml_device_is_blackwell(void) {
 
 extern "C" size_t gml_mmtm_fwd_workspace_bytes(const gml_mmtm_dims* dims) {
   (void)dims;
-  return 256;  // reserved (the current kernels keep everything in the caller-visible outputs)
+  return gemm_workspace_bytes();  // split-K partials of the FC GEMMs (streaming path)
 }
 
 extern "C" int gml_mmtm_gates(const float* a, const float* b, const float* w_sq, const float* b_sq, const float* w_v,
                               const float* b_v, const float* w_s, const float* b_s, float* z, float* h, float* g_a,
                               float* g_b, float* gate_sum, const float* m_a, const float* m_b, void* workspace,
                               size_t workspace_bytes, const gml_mmtm_dims* dims, int mode, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   Dims d;
   GML_TRY(check_dims(dims, mode, &d));
   if (!a || !b || !w_sq || !b_sq || !w_v || !b_v || !w_s || !b_s || !z || !h || !g_a || !g_b) return GML_E_BADARG;
   if (mode == GML_MODE_XMODAL_OFF && (!m_a || !m_b)) return GML_E_BADARG;
   if (d.n == 0) return GML_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GML_TRY(gates_chunk(a, b, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, m_a, m_b, d, mode, 0, d.n, false, st));
+  GML_TRY(gates_chunk(a, b, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, m_a, m_b, d, mode, 0, d.n, false, st,
+                      workspace, workspace_bytes));
   if (gate_sum) GML_TRY(launch_colsum(g_a, d.n, d.c_v, d.c_v, gate_sum, st));
   return GML_OK;
 }
@@ -283,7 +286,6 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
                             float* z, float* h, float* g_a, float* g_b, float* gate_sum, float* run_v, float* run_s,
                             int64_t step, const float* m_a, const float* m_b, void* workspace, size_t workspace_bytes,
                             const gml_mmtm_dims* dims, int mode, float gate_scale, uint32_t flags, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   Dims d;
   GML_TRY(check_dims(dims, mode, &d));
   if (!a || !b || !a_out || !b_out || !w_sq || !b_sq || !w_v || !b_v || !w_s || !b_s || !z || !h || !g_a || !g_b ||
@@ -315,7 +317,8 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
   const bool keep = true;
   for (int n0 = 0; n0 < d.n; n0 += cs) {
     const int cn = (d.n - n0) < cs ? (d.n - n0) : cs;
-    GML_TRY(gates_chunk(a, b, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, m_a, m_b, d, mode, n0, cn, keep, st));
+    GML_TRY(gates_chunk(a, b, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, m_a, m_b, d, mode, n0, cn, keep, st,
+                        workspace, workspace_bytes));
     // live sides can be gated right away; a substituted side waits for the running mean
     GML_TRY(apply_chunk(a, b, a_out, b_out, g_a, g_b, run_v, run_s, d, mode, gate_scale, n0, cn, live_a(mode),
                         live_b(mode), st));
@@ -335,7 +338,7 @@ extern "C" size_t gml_mmtm_bwd_workspace_bytes(const gml_mmtm_dims* dims) {
   if (!dims || dims->n < 0) return 0;
   const size_t n = (size_t)dims->n, ldz = (size_t)dims->c_v + dims->c_s, dd = (size_t)dims->d;
   // de_a [N,c_v] + de_b [N,c_s] + dh [2N,D] + dz [2N,ldz]   (2N rows cover mode 3)
-  return 256 + sizeof(float) * (n * ldz + 2 * n * dd + 2 * n * ldz) + 4 * 256;
+  return 256 + sizeof(float) * (n * ldz + 2 * n * dd + 2 * n * ldz) + 4 * 256 + gemm_workspace_bytes();
 }
 
 extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a, const float* b, const float* w_sq,
@@ -365,6 +368,8 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   float* de_b = carve((size_t)d.n * d.c_s);
   float* dh = carve((size_t)2 * d.n * d.d);
   float* dz = carve((size_t)2 * d.n * d.ldz);
+  void* gws = wp;
+  const size_t gws_bytes = gemm_workspace_bytes();
 
   const bool can_fuse = !(flags & GML_F_FORCE_STREAMING) && la && lb &&
                         fused_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
@@ -396,16 +401,16 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
       if (x3) {  // two independent hidden states
         ga.act = kActReluMask;
         GemmDesc both[2] = {ga, gb};
-        GML_TRY(launch_gemm(both, 2, st));
+        GML_TRY(launch_gemm(both, 2, st, gws, gws_bytes));
       } else if (la && lb) {
-        GML_TRY(launch_gemm(&ga, 1, st));
+        GML_TRY(launch_gemm(&ga, 1, st, gws, gws_bytes));
         gb.beta = 1;
-        GML_TRY(launch_gemm(&gb, 1, st));
+        GML_TRY(launch_gemm(&gb, 1, st, gws, gws_bytes));
       } else if (la) {
         ga.act = kActReluMask;
-        GML_TRY(launch_gemm(&ga, 1, st));
+        GML_TRY(launch_gemm(&ga, 1, st, gws, gws_bytes));
       } else {
-        GML_TRY(launch_gemm(&gb, 1, st));
+        GML_TRY(launch_gemm(&gb, 1, st, gws, gws_bytes));
       }
       // 3. dZ = dH Wsq
       GemmDesc gz[2];
@@ -417,7 +422,7 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
         gz[1].c = dz + (size_t)(d.hoff + n0) * d.ldz;
         cz = 2;
       }
-      GML_TRY(launch_gemm(gz, cz, st));
+      GML_TRY(launch_gemm(gz, cz, st, gws, gws_bytes));
       // 4. d_input = grad_out * scale + ds / HW
       ScaleSeg sa{go_a + oa, d_a + oa, la ? g_a + (size_t)n0 * d.c_v : run_v, dz + (size_t)n0 * d.ldz, cn * d.c_v,
                   d.hw_v, d.c_v, la ? 0 : 1, d.ldz, 0, gate_scale};
@@ -439,10 +444,10 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
     if (lb) gw[cw++] = GemmDesc{de_b, h + (size_t)d.hoff * d.d, d_w_s, nullptr, nullptr, d.c_s, d.d, d.n, d.c_s, d.d, d.d, 0, 0, 0, kActNone, 0};
     else GML_TRY(launch_fill_zero(d_w_s, (size_t)d.c_s * d.d, st));
   }
-  if (cw) GML_TRY(launch_gemm(gw, cw, st));
+  if (cw) GML_TRY(launch_gemm(gw, cw, st, gws, gws_bytes));
   if (d_w_sq) {
     GemmDesc gq{dh, z, d_w_sq, nullptr, nullptr, d.d, d.ldz, d.zrows, d.d, d.ldz, d.ldz, 0, 0, 0, kActNone, 0};
-    GML_TRY(launch_gemm(&gq, 1, st));
+    GML_TRY(launch_gemm(&gq, 1, st, gws, gws_bytes));
   }
   if (d_b_v) {
     if (la) GML_TRY(launch_colsum(de_a, d.n, d.c_v, d.c_v, d_b_v, st));

@@ -186,8 +186,12 @@ __global__ void fill_zero_kernel(float* p, size_t n) {
 
 }  // namespace
 
-int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st) {
+int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st, void* ws, size_t ws_bytes) {
   if (count < 1 || count > 2) return GML_E_BADARG;
+  {
+    const int rc = launch_gemm_pipelined(descs, count, ws, ws_bytes, st);
+    if (rc != GML_E_UNSUPPORTED) return rc;
+  }
   GemmBatch batch;
   int max_m = 0, max_n = 0;
   for (int i = 0; i < count; ++i) {

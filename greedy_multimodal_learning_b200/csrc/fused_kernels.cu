@@ -38,6 +38,7 @@ namespace gml {
 
 int g_fused_cluster = 0;   // tunables (gml_set_tunable): 0 = automatic
 int g_fused_threads = 0;
+long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
 namespace {
 
@@ -56,7 +57,14 @@ struct FusedCfg {
   int nchunk;    // pl / pc
   int n_groups;
   size_t data_bytes;
+  long long* trace;  // nullptr unless phase tracing is on: [cta < 8][iter < 16][16 stamps]
 };
+
+#define GML_STAMP(k)                                                                       \
+  do {                                                                                     \
+    if (f.trace && threadIdx.x == 0 && blockIdx.x < 8 && iter < 16)                        \
+      f.trace[((size_t)blockIdx.x * 16 + iter) * 16 + (k)] = clock64();                     \
+  } while (0)
 
 // ---- PTX wrappers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -157,7 +165,9 @@ __device__ __forceinline__ void issue_chunks(const FusedCfg& f, const Smem& s, c
 __device__ __forceinline__ void plane_drained(const FusedCfg& f, const Smem& s, int p, const float* xa, const float* xb,
                                               int rank, int next_n0, int next_gcount, uint64_t policy) {
   const int j = p / f.pc;
-  __threadfence_block();  // this group's shared-memory reads are done before the count is published
+  // No fence here on purpose: every shared-memory read of this plane has already returned its value
+  // (the stores that consume them have been issued), and a MEMBAR would also wait for those global
+  // stores to be acknowledged -- a full round trip per plane.
   const int prev = atomicAdd(&s.done[j], 1);
   if (prev == f.pc - 1) {
     s.done[j] = 0;
@@ -289,12 +299,13 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const 
   const int lane = tid % L, grp_in_pass = tid / L;
   const int hw4 = f.hw >> 2;
   uint32_t parity = 0;
+  int iter = 0;
 
   for (int grp = cluster_id; grp < f.n_groups; grp += n_clusters) {
     const int n0 = grp * f.g;
     const int gcount = min(f.g, f.n - n0);
     const int vplanes = gcount * 2 * f.cq;
-    const int vchunks = vplanes / f.pc;
+    GML_STAMP(0);
 
     // ---- pass 1: plane sums straight out of shared memory as chunks land --------------------
     // group gi owns planes gi, gi + NG, ...: every warp has work in every chunk wave
@@ -310,7 +321,9 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const 
       const float t = group_sum<L>((a0 + a1) + (a2 + a3));
       if (lane == 0) s.psum[p] = t;
     }
+    GML_STAMP(1);
     __syncthreads();
+    GML_STAMP(2);
     // ---- squeeze vector -> every CTA of the cluster (DSMEM) + global z ------------------------
     for (int p = tid; p < vplanes; p += T) {
       int g, mod, cl;
@@ -321,6 +334,7 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const 
       a.z[(size_t)(n0 + g) * 2 * f.c + k] = mean;
     }
     cluster.sync();
+    GML_STAMP(3);
     // ---- FC1: my slice of the hidden units, H = relu(Wsq z + bsq) ------------------------------
     gemv_rows<T, GMAX>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
                        2 * f.c, gcount, [&](int r, const float* acc) {
@@ -333,7 +347,9 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const 
                            a.h[(size_t)(n0 + g) * f.d + dd] = hval;
                          }
                        });
+    GML_STAMP(4);
     cluster.sync();
+    GML_STAMP(5);
     // ---- FC2: gates of my channels, both modalities (rows [0,cq) = visual, [cq,2cq) = skeleton) --
     gemv_rows<T, GMAX>(
         [&](int r) {
@@ -350,7 +366,9 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const 
             gout[(size_t)(n0 + g) * f.c + ch] = gate;
           }
         });
+    GML_STAMP(6);
     __syncthreads();
+    GML_STAMP(7);
     // ---- pass 2: gate from shared memory, stream out; refill freed chunks with the next group --
     const int next = grp + n_clusters;
     const int next_n0 = next * f.g;
@@ -371,9 +389,11 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_fwd_kernel(const 
       if (L < 32) __syncwarp();
       if (lane == 0) plane_drained(f, s, p, a.a, a.b, rank, next_n0, next_gcount, pol_stream);
     }
-    // chunks beyond this group's valid range exist only if this group was partial = the last one
+    GML_STAMP(8);
     __syncthreads();  // all refills of this iteration are issued; psum/scale may be reused
+    GML_STAMP(9);
     parity ^= 1;
+    ++iter;
   }
   cluster.sync();  // nobody exits while a sibling may still address its shared memory
 }
@@ -404,12 +424,13 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
   const int ncol_h = f.dq;        // outputs of the dH GEMV handled by this CTA
   const int ncol_z = 2 * f.cq;    // outputs of the dZ GEMV handled by this CTA
   uint32_t parity = 0;
+  int iter = 0;
 
   for (int grp = cluster_id; grp < f.n_groups; grp += n_clusters) {
     const int n0 = grp * f.g;
     const int gcount = min(f.g, f.n - n0);
     const int vplanes = gcount * 2 * f.cq;
-    const int vchunks = vplanes / f.pc;
+    GML_STAMP(0);
 
     // ---- early, latency-hiding loads of the per-plane gate and my slice of the ReLU mask -------
     float gate_pf = 0.f, h_pf = 0.f;
@@ -457,7 +478,9 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
       const float t = group_sum<L>((a0 + a1) + (a2 + a3));
       if (lane == 0) s.psum[p] = t;
     }
+    GML_STAMP(1);
     __syncthreads();
+    GML_STAMP(2);
     // ---- dE of my channels -> all CTAs + global ------------------------------------------------
     if (tid < vplanes) {
       const int p = tid;
@@ -473,6 +496,7 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
     }
     for (int i = tid; i < T * GMAX; i += T) s.part[i] = 0.f;
     cluster.sync();
+    GML_STAMP(3);
     // ---- dH for my slice of the hidden units: dE_a Wv + dE_b Ws, masked by H > 0 ----------------
     gemv_cols_partial<T, GMAX>(a.w_v, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
     gemv_cols_partial<T, GMAX>(a.w_s, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount, s.part);
@@ -489,7 +513,9 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
         a.dh[(size_t)(n0 + g) * f.d + dd] = v;
       }
     }
+    GML_STAMP(4);
     cluster.sync();
+    GML_STAMP(5);
     // ---- dZ of my channels: dH Wsq[:, my columns] -----------------------------------------------
     {
       // columns of this CTA: [rank*cq, +cq) of the visual half and [C + rank*cq, +cq) of the skeleton half
@@ -519,7 +545,9 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
         s.addv[(g * 2 + mod) * f.cq + cl] = v / (float)f.hw;  // MeanBackward: grad / HW
       }
     }
+    GML_STAMP(6);
     __syncthreads();
+    GML_STAMP(7);
     // ---- pass 2: d_input = grad_out * scale + ds / HW, refill with the next group ---------------
     const int next = grp + n_clusters;
     const int next_n0 = next * f.g;
@@ -540,8 +568,11 @@ __global__ void __launch_bounds__(T, (T == 256 ? 2 : 1)) fused_bwd_kernel(const 
       if (L < 32) __syncwarp();
       if (lane == 0) plane_drained(f, s, p, a.go_a, a.go_b, rank, next_n0, next_gcount, pol_stream);
     }
+    GML_STAMP(8);
     __syncthreads();
+    GML_STAMP(9);
     parity ^= 1;
+    ++iter;
   }
   cluster.sync();
 }
@@ -573,6 +604,7 @@ bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out
   if (((size_t)pc * hw * 4) % 16 != 0 || (size_t)pc * hw * 4 >= (1u << 20)) return false;  // mbarrier tx-count range
   f.n_groups = (n + f.g - 1) / f.g;
   f.data_bytes = (size_t)f.pl * hw * sizeof(float);
+  f.trace = g_fused_trace;
   const size_t total = f.data_bytes + extras_bytes(f, true);
   if (total > (cs == 4 ? 232448u : 115000u)) return false;
   *out = f;

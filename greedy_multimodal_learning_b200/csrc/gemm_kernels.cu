@@ -1,0 +1,271 @@
+// Pipelined fp32 SGEMM for the batched squeeze/excitation FCs and their gradients.
+//
+// The FC problems of an MMTM block are small (M = batch <= ~1k, N, K in {128..1024}): with one
+// 64x64 tile per CTA there are far fewer tiles than SMs and every tile walks a long, latency-bound
+// K loop.  This kernel therefore
+//   * splits K across CTAs (split-K) so that ~2 CTAs per SM are busy, and
+//   * feeds each CTA through a 3-stage cp.async (LDGSTS) pipeline, operands kept in their natural
+//     layout in shared memory (no register transpose), read back conflict-free as 128-bit vectors.
+// Split-K partials go to a caller-provided workspace; the LAST CTA to finish a tile (ticket
+// counter) adds the partials in split order -- a fixed order, so results are bit-reproducible --
+// and applies the epilogue (bias / ReLU / sigmoid / ReLU-mask / accumulate).
+// CUDA cores on purpose: 1e-5 fp32 parity with the reference's Linear layers (see fc_kernels.cu).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gml {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, STAGES = 3, THREADS = 256;
+constexpr int PITCH_KC = BK + 4;   // [row][k] rows of 16 floats, pitch 20 -> conflict-free 128-bit reads
+constexpr int PITCH_MN = BM + 4;   // [k][row] rows of 64 floats, pitch 68
+constexpr int TILE_FLOATS = (BM * PITCH_KC > BK * PITCH_MN) ? BM * PITCH_KC : BK * PITCH_MN;  // 1280
+
+struct PipeBatch {
+  GemmDesc d[2];
+  float* part[2];        // split-K partials per problem: [splits][m][n]
+  unsigned int* tickets; // [count][tiles_m * tiles_n]
+  int splits;
+  int k_per_split;       // multiple of BK
+};
+
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// one operand tile for k in [k0, k0 + BK): KC = k-contiguous source (src[t * ld + k]), else src[k * ld + t]
+template <bool KC>
+__device__ __forceinline__ void load_tile(float* s, const float* __restrict__ src, int ld, int t0, int tmax, int k0,
+                                          int kmax, int tid) {
+  if (KC) {
+    const int row = tid >> 2, kc = (tid & 3) * 4;
+    const int t = t0 + row, k = k0 + kc;
+    int bytes = (t < tmax) ? (kmax - k) * 4 : 0;
+    bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+    const float* g = bytes > 0 ? src + (size_t)t * ld + k : src;
+    cp_async16(s + row * PITCH_KC + kc, g, bytes);
+  } else {
+    const int kk = tid >> 4, tq = (tid & 15) * 4;
+    const int k = k0 + kk, t = t0 + tq;
+    int bytes = (k < kmax) ? (tmax - t) * 4 : 0;
+    bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+    const float* g = bytes > 0 ? src + (size_t)k * ld + t : src;
+    cp_async16(s + kk * PITCH_MN + tq, g, bytes);
+  }
+}
+
+// 4 (rows of this thread) x 4 (k) block of an operand tile
+template <bool KC>
+__device__ __forceinline__ void frag(const float* s, int t_idx, int kk, float (&v)[4][4]) {
+  if (KC) {  // rows t_idx + 16 i, vector along k
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(s + (t_idx + 16 * i) * PITCH_KC + kk);
+      v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+    }
+  } else {   // rows 4 t_idx + i, vector along rows
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(s + (kk + q) * PITCH_MN + t_idx * 4);
+      v[0][q] = t.x; v[1][q] = t.y; v[2][q] = t.z; v[3][q] = t.w;
+    }
+  }
+}
+
+__device__ __forceinline__ float epilogue(const GemmDesc& d, float v, int m, int n, const float* cp) {
+  if (d.beta) v += *cp;
+  if (d.bias) v += d.bias[n];
+  if (d.act == kActRelu) v = fmaxf(v, 0.f);
+  else if (d.act == kActSigmoid) v = sigmoidf_ref(v);
+  else if (d.act == kActReluMask) v = d.mask[(size_t)m * d.ldmask + n] > 0.f ? v : 0.f;
+  return v;
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(THREADS) gemm_pipe_kernel(const PipeBatch pb) {
+  __shared__ __align__(16) float As[STAGES][TILE_FLOATS];
+  __shared__ __align__(16) float Bs[STAGES][TILE_FLOATS];
+  __shared__ unsigned int s_ticket;
+  const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
+  const GemmDesc d = prob ? pb.d[1] : pb.d[0];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= d.m || n0 >= d.n) return;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k_begin = split * pb.k_per_split;
+  const int k_end = min(d.k, k_begin + pb.k_per_split);
+  const int nk = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) {
+      load_tile<A_KC>(As[s], d.a, d.lda, m0, d.m, k_begin + s * BK, k_end, tid);
+      load_tile<B_KC>(Bs[s], d.b, d.ldb, n0, d.n, k_begin + s * BK, k_end, tid);
+    }
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int nxt = kt + STAGES - 1;
+    if (nxt < nk) {
+      load_tile<A_KC>(As[nxt % STAGES], d.a, d.lda, m0, d.m, k_begin + nxt * BK, k_end, tid);
+      load_tile<B_KC>(Bs[nxt % STAGES], d.b, d.ldb, n0, d.n, k_begin + nxt * BK, k_end, tid);
+    }
+    cp_async_commit();
+    const float* as = As[kt % STAGES];
+    const float* bs = Bs[kt % STAGES];
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      float av[4][4], bv[4][4];
+      frag<A_KC>(as, ty, kk, av);
+      frag<B_KC>(bs, tx, kk, bv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i][q], bv[j][q], acc[i][j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  auto row_of = [&](int i) { return m0 + (A_KC ? ty + 16 * i : ty * 4 + i); };
+  auto col_of = [&](int j) { return n0 + (B_KC ? tx + 16 * j : tx * 4 + j); };
+
+  if (pb.splits == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = row_of(i);
+      if (m >= d.m) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = col_of(j);
+        if (n >= d.n) continue;
+        float* cp = d.c + (size_t)m * d.ldc + n;
+        *cp = epilogue(d, acc[i][j], m, n, cp);
+      }
+    }
+    return;
+  }
+  // split-K: publish my partial, the last CTA of this tile folds all partials in split order
+  float* part = pb.part[prob];
+  const size_t plane = (size_t)d.m * d.n;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = row_of(i);
+    if (m >= d.m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = col_of(j);
+      if (n < d.n) __stcg(part + (size_t)split * plane + (size_t)m * d.n + n, acc[i][j]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  unsigned int* ticket = pb.tickets + (size_t)prob * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x;
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)pb.splits - 1) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = row_of(i);
+    if (m >= d.m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = col_of(j);
+      if (n >= d.n) continue;
+      float v = 0.f;
+      for (int s = 0; s < pb.splits; ++s) v += __ldcg(part + (size_t)s * plane + (size_t)m * d.n + n);
+      float* cp = d.c + (size_t)m * d.ldc + n;
+      *cp = epilogue(d, v, m, n, cp);
+    }
+  }
+  if (tid == 0) *ticket = 0u;  // self-resetting: the workspace can be reused by the next launch
+}
+
+bool pipe_ok(const GemmDesc& d) {
+  // cp.async moves 16-byte chunks: bases 16-byte aligned, leading dimensions and (for k-contiguous
+  // operands) K multiples of 4
+  if (!aligned16(d.a) || !aligned16(d.b) || d.lda % 4 || d.ldb % 4) return false;
+  if ((d.a_kc || d.b_kc) && d.k % 4) return false;
+  return true;
+}
+
+}  // namespace
+
+size_t gemm_workspace_bytes() {
+  // Split-K is only used while tiles < 2 * SMs, with splits <= ceil(2 * SMs / tiles): the partial planes
+  // never exceed (2 * SMs + tiles) tiles of 64 x 64 floats, i.e. < 4 * SMs tiles; plus the ticket block.
+  return (size_t)4 * kNumSMs * BM * BN * sizeof(float) + 65536 + 1024;
+}
+
+// returns GML_E_UNSUPPORTED when the problems do not meet the pipeline's alignment rules
+int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (count < 1 || count > 2) return GML_E_BADARG;
+  PipeBatch pb;
+  int max_m = 0, max_n = 0, min_k = 1 << 30;
+  for (int i = 0; i < count; ++i) {
+    if (descs[i].m <= 0 || descs[i].n <= 0 || descs[i].k <= 0) return GML_E_BADARG;
+    if (!pipe_ok(descs[i])) return GML_E_UNSUPPORTED;
+    if (descs[i].a_kc != descs[0].a_kc || descs[i].b_kc != descs[0].b_kc) return GML_E_UNSUPPORTED;
+    pb.d[i] = descs[i];
+    max_m = descs[i].m > max_m ? descs[i].m : max_m;
+    max_n = descs[i].n > max_n ? descs[i].n : max_n;
+    min_k = descs[i].k < min_k ? descs[i].k : min_k;
+  }
+  if (count == 1) pb.d[1] = descs[0];
+  if (count == 2 && descs[0].k != descs[1].k) return GML_E_UNSUPPORTED;
+  const int tiles_m = ceil_div(max_m, BM), tiles_n = ceil_div(max_n, BN);
+  const long tiles = (long)tiles_m * tiles_n * count;
+  const int nk = ceil_div(min_k, BK);
+  int splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
+  if (splits > nk / 4) splits = nk / 4;  // at least 4 k-tiles per split
+  if (splits > 16) splits = 16;
+  if (splits < 1) splits = 1;
+  const size_t ticket_bytes = round_up((size_t)tiles * sizeof(unsigned int), 256);
+  while (splits > 1) {
+    size_t need = ticket_bytes;
+    for (int i = 0; i < count; ++i) need += round_up((size_t)splits * descs[i].m * descs[i].n * sizeof(float), 256);
+    if (ws && need <= ws_bytes) break;
+    --splits;
+  }
+  pb.splits = splits;
+  pb.k_per_split = ceil_div(nk, splits) * BK;
+  pb.tickets = nullptr;
+  pb.part[0] = pb.part[1] = nullptr;
+  if (splits > 1) {
+    char* p = static_cast<char*>(ws);
+    pb.tickets = reinterpret_cast<unsigned int*>(p);
+    p += ticket_bytes;
+    for (int i = 0; i < count; ++i) {
+      pb.part[i] = reinterpret_cast<float*>(p);
+      p += round_up((size_t)splits * descs[i].m * descs[i].n * sizeof(float), 256);
+    }
+    GML_CUDA_TRY(cudaMemsetAsync(pb.tickets, 0, ticket_bytes, st));
+  }
+  dim3 grid(tiles_n, tiles_m, count * splits);
+  {
+    LaunchScope ls(kTagGemm, st);
+    const bool akc = descs[0].a_kc != 0, bkc = descs[0].b_kc != 0;
+    if (akc && bkc) gemm_pipe_kernel<true, true><<<grid, THREADS, 0, st>>>(pb);
+    else if (akc && !bkc) gemm_pipe_kernel<true, false><<<grid, THREADS, 0, st>>>(pb);
+    else if (!akc && bkc) gemm_pipe_kernel<false, true><<<grid, THREADS, 0, st>>>(pb);
+    else gemm_pipe_kernel<false, false><<<grid, THREADS, 0, st>>>(pb);
+  }
+  GML_LAUNCH_CHECK();
+  return GML_OK;
+}
+
+}  // namespace gml

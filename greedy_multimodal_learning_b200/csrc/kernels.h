@@ -62,8 +62,12 @@ struct GemmDesc {
   int act;
   int beta;           // 0 or 1
 };
-// up to two independent problems in one launch (blockIdx.z)
-int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st);
+// up to two independent problems in one launch (blockIdx.z).  With a workspace of
+// gemm_workspace_bytes() the pipelined split-K kernel (gemm_kernels.cu) is used whenever the operands
+// are 16-byte aligned; otherwise the generic register-staged kernel (fc_kernels.cu).
+size_t gemm_workspace_bytes();
+int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st, void* ws = nullptr, size_t ws_bytes = 0);
 
 // out[j] = sum_i x[i*ld + j], i < rows, j < cols  (fixed order)
 int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st);

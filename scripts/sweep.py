@@ -21,8 +21,8 @@ from greedy_multimodal_learning_b200 import _lib as L  # noqa: E402
 VARIANTS = {
     # name: (flags, tunables)
     "stream_c40": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 40}),
-    "stream_c16": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 16}),
-    "stream_c80": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 80}),
+    "stream_c64": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 64}),
+    "stream_c100": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 100}),
     "stream_nochunk": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 100000}),
     "fused_cs4_t512": (L.F_FORCE_FUSED, {"fused_cluster": 4, "fused_threads": 512}),
     "fused_cs4_t256": (L.F_FORCE_FUSED, {"fused_cluster": 4, "fused_threads": 256}),
@@ -53,8 +53,8 @@ def main():
             def fwd(flags):
                 return lib.gml_mmtm_fwd(P(b.a), P(b.b), P(b.a_out), P(b.b_out), P(w[0]), P(w[1]), P(w[2]), P(w[3]),
                                         P(w[4]), P(w[5]), P(b.z), P(b.hid), P(b.g_a), P(b.g_b), P(b.gate_sum),
-                                        P(b.run_v), P(b.run_s), 0, None, None, None, 0, b.dims, 0, 1.0, flags,
-                                        stream.cuda_stream)
+                                        P(b.run_v), P(b.run_s), 0, None, None, P(b.fws), b.fws_bytes, b.dims, 0, 1.0,
+                                        flags, stream.cuda_stream)
 
             def bwd(flags):
                 return lib.gml_mmtm_bwd(P(b.go_a), P(b.go_b), P(b.a), P(b.b), P(w[0]), P(w[2]), P(w[4]), P(b.z),
@@ -64,7 +64,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 40, "fused_cluster": 0, "fused_threads": 0, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_cluster": 0, "fused_threads": 0, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 rc = fwd(flags)
                 if rc == -5:

@@ -242,7 +242,7 @@ def test_unaligned_pointers_through_the_c_abi():
     dims = _lib.MMTMDims(n, c, c, hw, hw, d)
     P = _lib.ptr
     _lib.check(lib.gml_mmtm_fwd(P(a), P(b), P(a_out), P(b_out), *[P(t) for t in w], P(z), P(h), P(g_a), P(g_b), P(gs),
-                                P(rv), P(rs_), 0, None, None, None, 0, dims, 0, 1.0, 0,
+                                P(rv), P(rs_), 0, None, None, None, 0, dims, 0, 1.0, 0,  # no workspace: split-K off
                                 _lib.current_stream(torch.device(DEV))))
     o = mo.forward_backward(x["A"], x["B"], p, mo.MMTMState.zeros(c), x["gA"], x["gB"])
     assert_close(a_out, o["A_out"], 1e-5, "A_out")
