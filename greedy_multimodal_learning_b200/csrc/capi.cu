@@ -218,6 +218,7 @@ namespace gml {
 extern int g_fused_cluster;
 extern int g_fused_threads;
 extern long long* g_fused_trace;
+extern int g_fused_kind;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -225,6 +226,10 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "fused_cluster")) {
     if (value != 0 && value != 4 && value != 8) return GML_E_BADARG;
     g_fused_cluster = (int)value; return GML_OK;
+  }
+  if (!strcmp(name, "fused_kind")) {
+    if (value < 0 || value > 2) return GML_E_BADARG;
+    g_fused_kind = (int)value; return GML_OK;
   }
   if (!strcmp(name, "fused_trace_ptr")) { g_fused_trace = reinterpret_cast<long long*>(value); return GML_OK; }
   if (!strcmp(name, "fused_threads")) {

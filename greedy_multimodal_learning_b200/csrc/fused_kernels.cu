@@ -38,6 +38,7 @@ namespace gml {
 
 int g_fused_cluster = 0;   // tunables (gml_set_tunable): 0 = automatic
 int g_fused_threads = 0;
+int g_fused_kind = 0;      // 0 auto, 1 shared-memory resident, 2 L2 resident
 long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
 namespace {
@@ -691,13 +692,367 @@ int dispatch_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
 #undef GML_BWD
 }
 
+
+// =============================================================================================
+// "L2-resident" variant: same cluster decomposition and exchange, but the planes are NOT parked
+// in shared memory.  Pass 1 streams them from HBM with an L2 evict_last hint, pass 2 re-reads them
+// (L2 hits, demoted with evict_first) a few microseconds later.  Shared memory use is a few KB, so
+// four CTAs (four independent groups) share an SM and the FC / cluster-barrier chain of one group
+// hides behind the streaming of the others.  One cluster per group, no persistent loop.
+// The in-flight footprint is (resident CTAs) x (slice per CTA) ~ 60 MB of the 126 MB L2.
+// =============================================================================================
+struct L2Smem {
+  float* vec_a; float* vec_b; float* psum; float* scale; float* addv; float* bias_h; float* bias_g; float* part;
+};
+__host__ __device__ inline size_t l2_smem_bytes(const FusedCfg& f, bool bwd) {
+  size_t b = (size_t)f.g * 2 * f.c * 4 + (size_t)f.g * f.d * 4 + 3 * (size_t)f.pl * 4 + ((size_t)f.dq + 2 * f.cq) * 4;
+  if (bwd) b += (size_t)f.threads * f.g * 4;
+  return b + 16;
+}
+__device__ __forceinline__ L2Smem l2_carve(unsigned char* p, const FusedCfg& f) {
+  L2Smem s;
+  s.vec_a = reinterpret_cast<float*>(p); p += (size_t)f.g * 2 * f.c * 4;
+  s.vec_b = reinterpret_cast<float*>(p); p += (size_t)f.g * f.d * 4;
+  s.psum = reinterpret_cast<float*>(p); p += f.pl * 4;
+  s.scale = reinterpret_cast<float*>(p); p += f.pl * 4;
+  s.addv = reinterpret_cast<float*>(p); p += f.pl * 4;
+  s.bias_h = reinterpret_cast<float*>(p); p += f.dq * 4;
+  s.bias_g = reinterpret_cast<float*>(p); p += 2 * f.cq * 4;
+  s.part = reinterpret_cast<float*>(p);
+  return s;
+}
+
+template <int T, int L, int GMAX>
+__global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, const FusedCfg f) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int grp = blockIdx.x / f.cs;
+  const L2Smem s = l2_carve(smem_raw, f);
+  const int tid = threadIdx.x;
+  const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
+  for (int i = tid; i < f.dq; i += T) s.bias_h[i] = __ldg(a.b_sq + rank * f.dq + i);
+  for (int i = tid; i < 2 * f.cq; i += T)
+    s.bias_g[i] = __ldg((i < f.cq ? a.b_v : a.b_s) + rank * f.cq + (i < f.cq ? i : i - f.cq));
+
+  constexpr int kPlanesPerPass = T / L;
+  const int lane = tid % L, grp_in_pass = tid / L;
+  const int hw4 = f.hw >> 2;
+  const int n0 = grp * f.g;
+  const int gcount = min(f.g, f.n - n0);
+  const int vplanes = gcount * 2 * f.cq;
+
+  // ---- pass 1: plane sums from HBM, lines asked to stay in L2 --------------------------------
+  for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
+    int g, mod, cl;
+    plane_coords(f, p, g, mod, cl);
+    const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) +
+                                                       ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i0 = 0; i0 < hw4; i0 += 8 * L) {
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + lane + u * L;
+        x[u] = i < hw4 ? ldg_hint(xv + i, pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a0 += x[u].x; a1 += x[u].y; a2 += x[u].z; a3 += x[u].w; }
+    }
+    const float t = group_sum<L>((a0 + a1) + (a2 + a3));
+    if (lane == 0) s.psum[p] = t;
+  }
+  cluster.sync();  // also: every CTA of the cluster is running before remote shared memory is touched
+  for (int p = tid; p < vplanes; p += T) {
+    int g, mod, cl;
+    plane_coords(f, p, g, mod, cl);
+    const int k = mod * f.c + rank * f.cq + cl;
+    const float mean = s.psum[p] / (float)f.hw;
+    for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + k] = mean;
+    a.z[(size_t)(n0 + g) * 2 * f.c + k] = mean;
+  }
+  cluster.sync();
+  gemv_rows_r<T, GMAX, 2>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
+                          2 * f.c, gcount, [&](int r, const float* acc) {
+                            const int dd = rank * f.dq + r;
+                            const float bias = s.bias_h[r];
+                            for (int g = 0; g < gcount; ++g) {
+                              const float hval = fmaxf(acc[g] + bias, 0.f);
+                              for (int dst = 0; dst < f.cs; ++dst)
+                                cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = hval;
+                              a.h[(size_t)(n0 + g) * f.d + dd] = hval;
+                            }
+                          });
+  cluster.sync();
+  gemv_rows_r<T, GMAX, 2>(
+      [&](int r) {
+        return r < f.cq ? a.w_v + (size_t)(rank * f.cq + r) * f.d : a.w_s + (size_t)(rank * f.cq + r - f.cq) * f.d;
+      },
+      2 * f.cq, f.d, s.vec_b, f.d, gcount, [&](int r, const float* acc) {
+        const int mod = r >= f.cq, cl = r - mod * f.cq;
+        const int ch = rank * f.cq + cl;
+        const float bias = s.bias_g[r];
+        float* gout = mod ? a.g_b : a.g_a;
+        for (int g = 0; g < gcount; ++g) {
+          const float gate = sigmoidf_ref(acc[g] + bias);
+          s.scale[(g * 2 + mod) * f.cq + cl] = gate * a.gate_scale;
+          gout[(size_t)(n0 + g) * f.c + ch] = gate;
+        }
+      });
+  __syncthreads();
+  // ---- pass 2: re-read (L2), gate, stream out ---------------------------------------------------
+  for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
+    int g, mod, cl;
+    plane_coords(f, p, g, mod, cl);
+    const float sc = s.scale[p];
+    const size_t off = ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
+    const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) + off);
+    float4* o = reinterpret_cast<float4*>((mod ? a.b_out : a.a_out) + off);
+    for (int i0 = 0; i0 < hw4; i0 += 8 * L) {
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + lane + u * L;
+        if (i < hw4) x[u] = ldg_hint(xv + i, pol_drop);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + lane + u * L;
+        if (i < hw4) {
+          x[u].x *= sc; x[u].y *= sc; x[u].z *= sc; x[u].w *= sc;
+          stg_stream(o + i, x[u]);
+        }
+      }
+    }
+  }
+  cluster.sync();  // nobody exits while a sibling may still address its shared memory
+}
+
+template <int T, int L, int GMAX>
+__global__ void __launch_bounds__(T, 4) l2_bwd_kernel(const FusedBwdArgs a, const FusedCfg f) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int grp = blockIdx.x / f.cs;
+  const L2Smem s = l2_carve(smem_raw, f);
+  const int tid = threadIdx.x;
+  const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
+  constexpr int kPlanesPerPass = T / L;
+  const int lane = tid % L, grp_in_pass = tid / L;
+  const int hw4 = f.hw >> 2;
+  const int ncol_h = f.dq, ncol_z = 2 * f.cq;
+  const int n0 = grp * f.g;
+  const int gcount = min(f.g, f.n - n0);
+  const int vplanes = gcount * 2 * f.cq;
+
+  float gate_pf = 0.f, h_pf = 0.f;
+  if (tid < vplanes) {
+    int g, mod, cl;
+    plane_coords(f, tid, g, mod, cl);
+    gate_pf = __ldg((mod ? a.g_b : a.g_a) + (size_t)(n0 + g) * f.c + rank * f.cq + cl);
+  }
+  if (tid < ncol_h * gcount) {
+    const int g = tid / ncol_h, col = tid - g * ncol_h;
+    h_pf = __ldg(a.h + (size_t)(n0 + g) * f.d + rank * f.dq + col);
+  }
+  // ---- pass 1: <grad_out (kept in L2), input (streamed once)> per plane --------------------------
+  for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
+    int g, mod, cl;
+    plane_coords(f, p, g, mod, cl);
+    const size_t off = ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
+    const float4* gv = reinterpret_cast<const float4*>((mod ? a.go_b : a.go_a) + off);
+    const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) + off);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i0 = 0; i0 < hw4; i0 += 4 * L) {
+      float4 x[4], gg[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + u * L;
+        if (i < hw4) {
+          gg[u] = ldg_hint(gv + i, pol_keep);
+          x[u] = ldg_hint(xv + i, pol_drop);
+        } else {
+          gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          x[u] = gg[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a0 = fmaf(gg[u].x, x[u].x, a0); a1 = fmaf(gg[u].y, x[u].y, a1);
+        a2 = fmaf(gg[u].z, x[u].z, a2); a3 = fmaf(gg[u].w, x[u].w, a3);
+      }
+    }
+    const float t = group_sum<L>((a0 + a1) + (a2 + a3));
+    if (lane == 0) s.psum[p] = t;
+  }
+  cluster.sync();
+  if (tid < vplanes) {
+    const int p = tid;
+    int g, mod, cl;
+    plane_coords(f, p, g, mod, cl);
+    const int ch = rank * f.cq + cl;
+    const float de = s.psum[p] * a.gate_scale * gate_pf * (1.f - gate_pf);
+    s.scale[p] = gate_pf * a.gate_scale;
+    for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + mod * f.c + ch] = de;
+    (mod ? a.de_b : a.de_a)[(size_t)(n0 + g) * f.c + ch] = de;
+  }
+  for (int i = tid; i < T * GMAX; i += T) s.part[i] = 0.f;
+  cluster.sync();
+  gemv_cols_partial<T, GMAX>(a.w_v, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
+  gemv_cols_partial<T, GMAX>(a.w_s, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount, s.part);
+  __syncthreads();
+  {
+    const int slices = T / ncol_h;
+    if (tid < ncol_h * gcount) {
+      const int g = tid / ncol_h, col = tid - g * ncol_h;
+      float v = 0.f;
+      for (int sl = 0; sl < slices; ++sl) v += s.part[((size_t)sl * GMAX + g) * ncol_h + col];
+      const int dd = rank * f.dq + col;
+      v = h_pf > 0.f ? v : 0.f;
+      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = v;
+      a.dh[(size_t)(n0 + g) * f.d + dd] = v;
+    }
+  }
+  cluster.sync();
+  {
+    const int slices = T / ncol_z;
+    const int col = tid % ncol_z, sl = tid / ncol_z;
+    const int gcol = (col < f.cq) ? rank * f.cq + col : f.c + rank * f.cq + (col - f.cq);
+    const int span = (f.d + slices - 1) / slices;
+    const int ka = sl * span, kb = min(f.d, ka + span);
+    float acc[GMAX];
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
+#pragma unroll 16
+    for (int kk = ka; kk < kb; ++kk) {
+      const float wv = __ldg(a.w_sq + (size_t)kk * 2 * f.c + gcol);
+#pragma unroll
+      for (int g = 0; g < GMAX; ++g)
+        if (g < gcount) acc[g] = fmaf(s.vec_b[g * f.d + kk], wv, acc[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g) s.part[((size_t)sl * GMAX + g) * ncol_z + col] = acc[g];
+    __syncthreads();
+    for (int o = tid; o < ncol_z * gcount; o += T) {
+      const int g = o / ncol_z, c2 = o - g * ncol_z;
+      float v = 0.f;
+      for (int s2 = 0; s2 < slices; ++s2) v += s.part[((size_t)s2 * GMAX + g) * ncol_z + c2];
+      const int mod = c2 >= f.cq, cl = c2 - mod * f.cq;
+      s.addv[(g * 2 + mod) * f.cq + cl] = v / (float)f.hw;
+    }
+  }
+  __syncthreads();
+  // ---- pass 2: d_input = grad_out (L2 re-read) * scale + ds / HW ---------------------------------
+  for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
+    int g, mod, cl;
+    plane_coords(f, p, g, mod, cl);
+    const float sc = s.scale[p], ad = s.addv[p];
+    const size_t off = ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
+    const float4* gv = reinterpret_cast<const float4*>((mod ? a.go_b : a.go_a) + off);
+    float4* o = reinterpret_cast<float4*>((mod ? a.d_b : a.d_a) + off);
+    for (int i0 = 0; i0 < hw4; i0 += 8 * L) {
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + lane + u * L;
+        if (i < hw4) x[u] = ldg_hint(gv + i, pol_drop);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + lane + u * L;
+        if (i < hw4) {
+          x[u].x = fmaf(x[u].x, sc, ad); x[u].y = fmaf(x[u].y, sc, ad);
+          x[u].z = fmaf(x[u].z, sc, ad); x[u].w = fmaf(x[u].w, sc, ad);
+          stg_stream(o + i, x[u]);
+        }
+      }
+    }
+  }
+  cluster.sync();
+}
+
+bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
+  if (n <= 0 || c % (4 * cs) != 0 || d % (4 * cs) != 0 || hw % 4 != 0) return false;
+  FusedCfg f;
+  f.n = n; f.c = c; f.hw = hw; f.d = d; f.cs = cs; f.threads = 256;
+  f.cq = c / cs; f.dq = d / cs;
+  const size_t slice = (size_t)2 * f.cq * hw * sizeof(float);
+  f.g = slice * 2 <= 131072 ? 2 : 1;  // two samples per cluster while the CTA's share stays <= 128 KB
+  if (f.g > n) f.g = n;
+  f.pl = f.g * 2 * f.cq;
+  if (f.pl > f.threads || f.dq * f.g > f.threads) return false;
+  if (f.dq > f.threads || 2 * f.cq > f.threads || f.threads % f.dq != 0 || f.threads % (2 * f.cq) != 0) return false;
+  f.pc = f.pl; f.nchunk = 1;
+  f.n_groups = (n + f.g - 1) / f.g;
+  f.data_bytes = 0;
+  f.trace = nullptr;
+  if ((long long)f.n_groups * cs > 0x7fffffffLL) return false;
+  *out = f;
+  return true;
+}
+
+template <typename Args, typename K>
+int do_launch_l2(K kern, const Args& args, const FusedCfg& f, bool bwd, cudaStream_t st, int tag) {
+  const size_t smem = l2_smem_bytes(f, bwd);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(f.threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = f.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3((unsigned)f.n_groups * f.cs);
+  {
+    LaunchScope ls(tag, st);
+    GML_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args, f));
+  }
+  GML_LAUNCH_CHECK();
+  return GML_OK;
+}
+template <typename Args>
+int dispatch_l2_fwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
+  const int l = lanes_for(f.hw);
+#define GML_L2F(LL, GG) return do_launch_l2(l2_fwd_kernel<256, LL, GG>, args, f, false, st, kTagFusedFwd)
+  if (f.g == 1) { if (l == 32) GML_L2F(32, 1); if (l == 16) GML_L2F(16, 1); GML_L2F(8, 1); }
+  if (l == 32) GML_L2F(32, 2);
+  if (l == 16) GML_L2F(16, 2);
+  GML_L2F(8, 2);
+#undef GML_L2F
+}
+template <typename Args>
+int dispatch_l2_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
+  const int l = lanes_for(f.hw);
+#define GML_L2B(LL, GG) return do_launch_l2(l2_bwd_kernel<256, LL, GG>, args, f, true, st, kTagFusedBwd)
+  if (f.g == 1) { if (l == 32) GML_L2B(32, 1); if (l == 16) GML_L2B(16, 1); GML_L2B(8, 1); }
+  if (l == 32) GML_L2B(32, 2);
+  if (l == 16) GML_L2B(16, 2);
+  GML_L2B(8, 2);
+#undef GML_L2B
+}
+
 }  // namespace
+
+static bool use_l2_kind() { return g_fused_kind == 2 || g_fused_kind == 0; }
+static bool pick_cfg(int n, int c, int hw, int d, FusedCfg* f, bool* l2) {
+  if (use_l2_kind()) {
+    const int cs = g_fused_cluster ? g_fused_cluster : 8;
+    if (make_cfg_l2(n, c, hw, d, cs, f) || (!g_fused_cluster && make_cfg_l2(n, c, hw, d, 4, f))) {
+      *l2 = true;
+      return true;
+    }
+    if (g_fused_kind == 2) return false;
+  }
+  *l2 = false;
+  return make_cfg(n, c, hw, d, f);
+}
 
 bool fused_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mode) {
   if (mode != GML_MODE_NORMAL) return false;
   if (c_v != c_s || hw_v != hw_s) return false;
   FusedCfg f;
-  if (!make_cfg(n, c_v, hw_v, d, &f)) return false;
+  bool l2 = false;
+  if (!pick_cfg(n, c_v, hw_v, d, &f, &l2)) return false;
   // per-sample FC weights are re-read from L2 for every group: only worth it while they are
   // small next to the group's feature-map bytes (MMTM4's 512x7^2 goes the streaming way)
   const double w_bytes = 4.0 * (2.0 * c_v * d + 2.0 * c_v * d);
@@ -707,19 +1062,23 @@ bool fused_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mod
 
 int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st) {
   FusedCfg f;
-  if (!make_cfg(args.n, args.c, args.hw, args.d, &f)) return GML_E_UNSUPPORTED;
+  bool l2 = false;
+  if (!pick_cfg(args.n, args.c, args.hw, args.d, &f, &l2)) return GML_E_UNSUPPORTED;
   if (!aligned16(args.a) || !aligned16(args.b) || !aligned16(args.a_out) || !aligned16(args.b_out) ||
       !aligned16(args.w_sq) || !aligned16(args.w_v) || !aligned16(args.w_s))
     return GML_E_UNSUPPORTED;
+  if (l2) return dispatch_l2_fwd(args, f, st);
   return f.threads == 512 ? dispatch_fwd<512>(args, f, st) : dispatch_fwd<256>(args, f, st);
 }
 
 int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st) {
   FusedCfg f;
-  if (!make_cfg(args.n, args.c, args.hw, args.d, &f)) return GML_E_UNSUPPORTED;
+  bool l2 = false;
+  if (!pick_cfg(args.n, args.c, args.hw, args.d, &f, &l2)) return GML_E_UNSUPPORTED;
   if (!aligned16(args.go_a) || !aligned16(args.go_b) || !aligned16(args.a) || !aligned16(args.b) ||
       !aligned16(args.d_a) || !aligned16(args.d_b))
     return GML_E_UNSUPPORTED;
+  if (l2) return dispatch_l2_bwd(args, f, st);
   return f.threads == 512 ? dispatch_bwd<512>(args, f, st) : dispatch_bwd<256>(args, f, st);
 }
 

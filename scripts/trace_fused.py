@@ -15,6 +15,7 @@ dev = torch.device("cuda:0")
 NAMES = ["pass1", "sync", "scatter+csync", "fc1", "csync", "fc2", "sync", "pass2", "sync"]
 for (c, h, n) in ((128, 28, 256), (256, 14, 256)):
     for cs, thr in ((4, 512), (8, 256)):
+        L.check(lib.gml_set_tunable(b"fused_kind", 1))
         L.check(lib.gml_set_tunable(b"fused_cluster", cs))
         L.check(lib.gml_set_tunable(b"fused_threads", thr))
         b = BlockBuffers(torch, L, n, c, h, dev, seed=c)

@@ -172,20 +172,23 @@ FUSED = [(1, 16, 4, 4), (2, 16, 4, 4), (3, 32, 8, 8), (5, 64, 6, 6), (7, 128, 28
 @pytest.fixture
 def fused_geometry(request):
     lib = _lib.load()
-    cs, threads = request.param
+    kind, cs, threads = request.param
+    _lib.check(lib.gml_set_tunable(b"fused_kind", kind))
     _lib.check(lib.gml_set_tunable(b"fused_cluster", cs))
     _lib.check(lib.gml_set_tunable(b"fused_threads", threads))
     yield request.param
+    _lib.check(lib.gml_set_tunable(b"fused_kind", 0))
     _lib.check(lib.gml_set_tunable(b"fused_cluster", 0))
     _lib.check(lib.gml_set_tunable(b"fused_threads", 0))
 
 
-@pytest.mark.parametrize("fused_geometry", [(4, 512), (4, 256), (8, 256)], indirect=True,
-                         ids=["cs4_t512", "cs4_t256", "cs8_t256"])
+# kind 1 = planes resident in shared memory (TMA + mbarrier), kind 2 = planes resident in L2
+@pytest.mark.parametrize("fused_geometry", [(1, 4, 512), (1, 4, 256), (1, 8, 256), (2, 8, 0), (2, 4, 0)], indirect=True,
+                         ids=["smem_cs4_t512", "smem_cs4_t256", "smem_cs8_t256", "l2_cs8", "l2_cs4"])
 @pytest.mark.parametrize("shape", FUSED, ids=lambda s: "n%dc%d_%dx%d" % s)
 def test_fused_cluster_kernels_vs_oracle(shape, fused_geometry):
     n, c, h, w = shape
-    if fused_geometry[0] == 8 and c % 32 != 0:
+    if fused_geometry[1] == 8 and c % 32 != 0:
         pytest.skip("8-CTA clusters need C % 32 == 0")
     rs = np.random.RandomState(n * 7 + c)
     t = lambda *s: torch.from_numpy(rs.standard_normal(s).astype(np.float32))
