@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, cons
       }
     }
   }
-  cluster.sync();  // nobody exits while a sibling may still address its shared memory
+  // no trailing cluster barrier: remote shared-memory writes only happen before the third barrier
 }
 
 template <int T, int L, int GMAX>
@@ -968,7 +968,7 @@ __global__ void __launch_bounds__(T, 4) l2_bwd_kernel(const FusedBwdArgs a, cons
       }
     }
   }
-  cluster.sync();
+  // no trailing cluster barrier (see forward)
 }
 
 bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
