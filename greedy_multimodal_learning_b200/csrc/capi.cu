@@ -219,6 +219,7 @@ extern int g_fused_cluster;
 extern int g_fused_threads;
 extern long long* g_fused_trace;
 extern int g_fused_kind;
+extern int g_fused_prefetch;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -231,6 +232,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
     if (value < 0 || value > 2) return GML_E_BADARG;
     g_fused_kind = (int)value; return GML_OK;
   }
+  if (!strcmp(name, "fused_prefetch")) { g_fused_prefetch = value ? 1 : 0; return GML_OK; }
   if (!strcmp(name, "fused_trace_ptr")) { g_fused_trace = reinterpret_cast<long long*>(value); return GML_OK; }
   if (!strcmp(name, "fused_threads")) {
     if (value != 0 && value != 256 && value != 512) return GML_E_BADARG;

@@ -39,6 +39,7 @@ namespace gml {
 int g_fused_cluster = 0;   // tunables (gml_set_tunable): 0 = automatic
 int g_fused_threads = 0;
 int g_fused_kind = 0;      // 0 auto, 1 shared-memory resident, 2 L2 resident
+int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch on/off (measured: no gain, off)
 long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
 namespace {
@@ -59,6 +60,7 @@ struct FusedCfg {
   int n_groups;
   size_t data_bytes;
   long long* trace;  // nullptr unless phase tracing is on: [cta < 8][iter < 16][16 stamps]
+  int prefetch;      // L2-resident kernels: issue bulk L2 prefetches of the CTA's planes up front
 };
 
 #define GML_STAMP(k)                                                                       \
@@ -97,6 +99,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
           smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
+}
+
+// fire-and-forget HBM -> L2 bulk prefetch (no registers, no shared memory, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy)
+               : "memory");
 }
 
 struct Smem {
@@ -606,6 +614,7 @@ bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out
   f.n_groups = (n + f.g - 1) / f.g;
   f.data_bytes = (size_t)f.pl * hw * sizeof(float);
   f.trace = g_fused_trace;
+  f.prefetch = 0;
   const size_t total = f.data_bytes + extras_bytes(f, true);
   if (total > (cs == 4 ? 232448u : 115000u)) return false;
   *out = f;
@@ -742,6 +751,15 @@ __global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, cons
   const int gcount = min(f.g, f.n - n0);
   const int vplanes = gcount * 2 * f.cq;
 
+  // ---- whole slice on its way HBM -> L2 before the first register load is issued ---------------
+  if (f.prefetch) {
+    for (int p = tid; p < vplanes; p += T) {
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      bulk_prefetch_l2((mod ? a.b : a.a) + ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw,
+                       (uint32_t)f.hw * 4u, pol_keep);
+    }
+  }
   // ---- pass 1: plane sums from HBM, lines asked to stay in L2 --------------------------------
   for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
     int g, mod, cl;
@@ -854,6 +872,15 @@ __global__ void __launch_bounds__(T, 4) l2_bwd_kernel(const FusedBwdArgs a, cons
   if (tid < ncol_h * gcount) {
     const int g = tid / ncol_h, col = tid - g * ncol_h;
     h_pf = __ldg(a.h + (size_t)(n0 + g) * f.d + rank * f.dq + col);
+  }
+  if (f.prefetch) {
+    for (int p = tid; p < vplanes; p += T) {
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      const size_t off = ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
+      bulk_prefetch_l2((mod ? a.go_b : a.go_a) + off, (uint32_t)f.hw * 4u, pol_keep);
+      bulk_prefetch_l2((mod ? a.b : a.a) + off, (uint32_t)f.hw * 4u, pol_drop);
+    }
   }
   // ---- pass 1: <grad_out (kept in L2), input (streamed once)> per plane --------------------------
   for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
@@ -986,6 +1013,7 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
   f.n_groups = (n + f.g - 1) / f.g;
   f.data_bytes = 0;
   f.trace = nullptr;
+  f.prefetch = g_fused_prefetch && ((size_t)hw * 4) % 16 == 0;
   if ((long long)f.n_groups * cs > 0x7fffffffLL) return false;
   *out = f;
   return true;
@@ -1034,13 +1062,21 @@ int dispatch_l2_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
 }  // namespace
 
 static bool use_l2_kind() { return g_fused_kind == 2 || g_fused_kind == 0; }
-static bool pick_cfg(int n, int c, int hw, int d, FusedCfg* f, bool* l2) {
+static bool weights_ok(const FusedCfg& f) {
+  // per-sample FC weights are re-read from L2 for every group: only worth it while they are small
+  // next to the group's feature-map bytes (MMTM4's 512x7^2 goes the streaming way)
+  const double w_bytes = 16.0 * f.c * f.d;
+  const double group_bytes = 2.0 * f.g * 2.0 * f.c * f.hw * 4.0;
+  return w_bytes <= group_bytes;
+}
+static bool pick_cfg(int n, int c, int hw, int d, FusedCfg* f, bool* l2, bool bwd) {
   if (use_l2_kind()) {
-    const int cs = g_fused_cluster ? g_fused_cluster : 8;
-    if (make_cfg_l2(n, c, hw, d, cs, f) || (!g_fused_cluster && make_cfg_l2(n, c, hw, d, 4, f))) {
-      *l2 = true;
-      return true;
-    }
+    // measured on B200 (profiles/): the forward prefers 8-CTA clusters (smaller L2 footprint in flight),
+    // the backward 4-CTA clusters (fewer, larger transposed GEMVs)
+    const int first = g_fused_cluster ? g_fused_cluster : (bwd ? 4 : 8);
+    const int second = g_fused_cluster ? 0 : (bwd ? 8 : 4);
+    if (make_cfg_l2(n, c, hw, d, first, f) && weights_ok(*f)) { *l2 = true; return true; }
+    if (second && make_cfg_l2(n, c, hw, d, second, f) && weights_ok(*f)) { *l2 = true; return true; }
     if (g_fused_kind == 2) return false;
   }
   *l2 = false;
@@ -1052,18 +1088,16 @@ bool fused_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mod
   if (c_v != c_s || hw_v != hw_s) return false;
   FusedCfg f;
   bool l2 = false;
-  if (!pick_cfg(n, c_v, hw_v, d, &f, &l2)) return false;
-  // per-sample FC weights are re-read from L2 for every group: only worth it while they are
-  // small next to the group's feature-map bytes (MMTM4's 512x7^2 goes the streaming way)
-  const double w_bytes = 4.0 * (2.0 * c_v * d + 2.0 * c_v * d);
-  const double group_bytes = 2.0 * f.g * 2.0 * c_v * hw_v * 4.0;
-  return w_bytes <= group_bytes;
+  if (!pick_cfg(n, c_v, hw_v, d, &f, &l2, false)) return false;
+  if (!weights_ok(f)) return false;
+  FusedCfg fb;
+  return pick_cfg(n, c_v, hw_v, d, &fb, &l2, true) && weights_ok(fb);
 }
 
 int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st) {
   FusedCfg f;
   bool l2 = false;
-  if (!pick_cfg(args.n, args.c, args.hw, args.d, &f, &l2)) return GML_E_UNSUPPORTED;
+  if (!pick_cfg(args.n, args.c, args.hw, args.d, &f, &l2, false)) return GML_E_UNSUPPORTED;
   if (!aligned16(args.a) || !aligned16(args.b) || !aligned16(args.a_out) || !aligned16(args.b_out) ||
       !aligned16(args.w_sq) || !aligned16(args.w_v) || !aligned16(args.w_s))
     return GML_E_UNSUPPORTED;
@@ -1074,7 +1108,7 @@ int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st) {
 int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st) {
   FusedCfg f;
   bool l2 = false;
-  if (!pick_cfg(args.n, args.c, args.hw, args.d, &f, &l2)) return GML_E_UNSUPPORTED;
+  if (!pick_cfg(args.n, args.c, args.hw, args.d, &f, &l2, true)) return GML_E_UNSUPPORTED;
   if (!aligned16(args.go_a) || !aligned16(args.go_b) || !aligned16(args.a) || !aligned16(args.b) ||
       !aligned16(args.d_a) || !aligned16(args.d_b))
     return GML_E_UNSUPPORTED;
