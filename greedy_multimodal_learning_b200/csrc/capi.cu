@@ -263,6 +263,7 @@ extern "C" int gml_mmtm_gates(const float* a, const float* b, const float* w_sq,
   if (mode == GML_MODE_XMODAL_OFF && (!m_a || !m_b)) return GML_E_BADARG;
   if (d.n == 0) return GML_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GML_TRY(prepare_gemm_workspace(workspace, workspace_bytes, st));
   GML_TRY(gates_chunk(a, b, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, m_a, m_b, d, mode, 0, d.n, false, st,
                       workspace, workspace_bytes));
   if (gate_sum) GML_TRY(launch_colsum(g_a, d.n, d.c_v, d.c_v, gate_sum, st));
@@ -313,11 +314,12 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
     FusedFwdArgs fa{a, b, a_out, b_out, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, run_v, run_s,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
     GML_TRY(launch_fused_fwd(fa, st));
-    GML_TRY(launch_colsum(g_a, d.n, d.c_v, d.c_v, gate_sum, st));
-    if (update) GML_TRY(launch_running_update(run_v, run_s, gate_sum, d.c_v, (double)d.n, (double)step, st));
-    return GML_OK;
+    ColsumSeg cs{g_a, gate_sum, d.n, d.c_v, d.c_v, update ? run_v : nullptr, update ? run_s : nullptr, (float)d.n,
+                 (float)step};
+    return launch_colsums(&cs, 1, st);
   }
 
+  GML_TRY(prepare_gemm_workspace(workspace, workspace_bytes, st));
   // Streaming path: batch chunks sized for L2 so the gating pass re-reads from L2.
   const size_t per_sample = ((size_t)d.c_v * d.hw_v + (size_t)d.c_s * d.hw_s) * sizeof(float);
   const int cs = chunk_samples(d, per_sample);
@@ -330,8 +332,11 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
     GML_TRY(apply_chunk(a, b, a_out, b_out, g_a, g_b, run_v, run_s, d, mode, gate_scale, n0, cn, live_a(mode),
                         live_b(mode), st));
   }
-  GML_TRY(launch_colsum(g_a, d.n, d.c_v, d.c_v, gate_sum, st));
-  if (update) GML_TRY(launch_running_update(run_v, run_s, gate_sum, d.c_v, (double)d.n, (double)step, st));
+  {
+    ColsumSeg cs{g_a, gate_sum, d.n, d.c_v, d.c_v, update ? run_v : nullptr, update ? run_s : nullptr, (float)d.n,
+                 (float)step};
+    GML_TRY(launch_colsums(&cs, 1, st));
+  }
   if (curate) {
     // balanced_mmtm.py:139-152: the substituted scale is the running mean INCLUDING this batch.
     // With GML_F_NO_RUNNING_UPDATE the caller has already folded the (all-reduced) batch in.
@@ -377,6 +382,7 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   float* dz = carve((size_t)2 * d.n * d.ldz);
   void* gws = wp;
   const size_t gws_bytes = gemm_workspace_bytes();
+  GML_TRY(prepare_gemm_workspace(gws, gws_bytes, st));
 
   const bool can_fuse = !(flags & GML_F_FORCE_STREAMING) && la && lb &&
                         fused_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
@@ -456,14 +462,19 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
     GemmDesc gq{dh, z, d_w_sq, nullptr, nullptr, d.d, d.ldz, d.zrows, d.d, d.ldz, d.ldz, 0, 0, 0, kActNone, 0};
     GML_TRY(launch_gemm(&gq, 1, st, gws, gws_bytes));
   }
-  if (d_b_v) {
-    if (la) GML_TRY(launch_colsum(de_a, d.n, d.c_v, d.c_v, d_b_v, st));
-    else GML_TRY(launch_fill_zero(d_b_v, d.c_v, st));
+  {
+    ColsumSeg segs[3];
+    int nseg = 0;
+    if (d_b_v) {
+      if (la) segs[nseg++] = ColsumSeg{de_a, d_b_v, d.n, d.c_v, d.c_v, nullptr, nullptr, 1.f, 0.f};
+      else GML_TRY(launch_fill_zero(d_b_v, d.c_v, st));
+    }
+    if (d_b_s) {
+      if (lb) segs[nseg++] = ColsumSeg{de_b, d_b_s, d.n, d.c_s, d.c_s, nullptr, nullptr, 1.f, 0.f};
+      else GML_TRY(launch_fill_zero(d_b_s, d.c_s, st));
+    }
+    if (d_b_sq) segs[nseg++] = ColsumSeg{dh, d_b_sq, d.zrows, d.d, d.d, nullptr, nullptr, 1.f, 0.f};
+    if (nseg) GML_TRY(launch_colsums(segs, nseg, st));
   }
-  if (d_b_s) {
-    if (lb) GML_TRY(launch_colsum(de_b, d.n, d.c_s, d.c_s, d_b_s, st));
-    else GML_TRY(launch_fill_zero(d_b_s, d.c_s, st));
-  }
-  if (d_b_sq) GML_TRY(launch_colsum(dh, d.zrows, d.d, d.d, d_b_sq, st));
   return GML_OK;
 }

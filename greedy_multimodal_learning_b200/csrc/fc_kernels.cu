@@ -143,21 +143,43 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_kernel(GemmBatch bat
   }
 }
 
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int rows, int cols, int ld,
-                                                     float* __restrict__ out) {
+struct ColsumBatch {
+  ColsumSeg seg[4];
+  int block_start[5];
+};
+
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumBatch b) {
   __shared__ float part[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + tx;
-  float a = 0.f;
-  if (j < cols)
-    for (int i = ty; i < rows; i += 8) a += x[(size_t)i * ld + j];
-  part[ty][tx] = a;
-  __syncthreads();
-  if (ty == 0 && j < cols) {
-    float s = 0.f;
+  int sid = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) s += part[r][tx];
-    out[j] = s;
+  for (int i = 1; i < 4; ++i)
+    if ((int)blockIdx.x >= b.block_start[i]) sid = i;
+  const ColsumSeg s = sid == 0 ? b.seg[0] : (sid == 1 ? b.seg[1] : (sid == 2 ? b.seg[2] : b.seg[3]));
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = (blockIdx.x - b.block_start[sid]) * 32 + tx;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (j < s.cols) {
+    int i = ty;
+    for (; i + 24 < s.rows; i += 32) {  // 4 independent loads in flight
+      a0 += s.x[(size_t)i * s.ld + j];
+      a1 += s.x[(size_t)(i + 8) * s.ld + j];
+      a2 += s.x[(size_t)(i + 16) * s.ld + j];
+      a3 += s.x[(size_t)(i + 24) * s.ld + j];
+    }
+    for (; i < s.rows; i += 8) a0 += s.x[(size_t)i * s.ld + j];
+  }
+  part[ty][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ty == 0 && j < s.cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += part[r][tx];
+    s.out[j] = t;
+    if (s.run_v) {
+      const float mean = t / s.n_total;
+      s.run_v[j] = (mean + s.run_v[j] * s.step) / (s.step + 1.f);
+      if (s.run_s) s.run_s[j] = (mean + s.run_s[j] * s.step) / (s.step + 1.f);
+    }
   }
 }
 
@@ -215,11 +237,30 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st, void* ws, siz
   return GML_OK;
 }
 
-int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st) {
+int launch_colsums(const ColsumSeg* segs, int count, cudaStream_t st) {
+  if (count < 1 || count > 4) return GML_E_BADARG;
+  ColsumBatch b;
+  int blocks = 0;
+  for (int i = 0; i < 4; ++i) {
+    b.block_start[i] = blocks;
+    if (i < count) {
+      b.seg[i] = segs[i];
+      blocks += ceil_div(segs[i].cols, 32);
+    } else {
+      b.seg[i] = segs[0];
+    }
+  }
+  b.block_start[4] = blocks;
+  for (int i = count; i < 4; ++i) b.block_start[i] = blocks;  // unreachable segments
   { LaunchScope ls(kTagSmall, st);
-  colsum_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(x, rows, cols, ld, out); }
+  colsum_kernel<<<blocks, 256, 0, st>>>(b); }
   GML_LAUNCH_CHECK();
   return GML_OK;
+}
+
+int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st) {
+  ColsumSeg s{x, out, rows, cols, ld, nullptr, nullptr, 1.f, 0.f};
+  return launch_colsums(&s, 1, st);
 }
 
 int launch_fill_rows(float* z, int rows, int ld, int off, const float* v, int cols, cudaStream_t st) {

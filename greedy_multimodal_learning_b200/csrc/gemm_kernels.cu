@@ -178,18 +178,41 @@ __global__ void __launch_bounds__(THREADS) gemm_pipe_kernel(const PipeBatch pb) 
   __syncthreads();
   if (s_ticket != (unsigned)pb.splits - 1) return;
   __threadfence();
+  // fold the partials in split order; all 16 loads of a split are issued together (L2 latency, not
+  // bandwidth, is the cost here), splits unrolled by two
+  float sum[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sum[i][j] = 0.f;
+  int rows[4], cols[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { rows[i] = row_of(i); cols[i] = col_of(i); }
+  for (int s0 = 0; s0 < pb.splits; s0 += 2) {
+    float v0[4][4], v1[4][4];
+    const bool two = s0 + 1 < pb.splits;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = rows[i] < d.m && cols[j] < d.n;
+        const size_t o = (size_t)rows[i] * d.n + cols[j];
+        v0[i][j] = ok ? __ldcg(part + (size_t)s0 * plane + o) : 0.f;
+        v1[i][j] = (ok && two) ? __ldcg(part + (size_t)(s0 + 1) * plane + o) : 0.f;
+      }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sum[i][j] = (sum[i][j] + v0[i][j]) + v1[i][j];
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = row_of(i);
-    if (m >= d.m) continue;
+    if (rows[i] >= d.m) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = col_of(j);
-      if (n >= d.n) continue;
-      float v = 0.f;
-      for (int s = 0; s < pb.splits; ++s) v += __ldcg(part + (size_t)s * plane + (size_t)m * d.n + n);
-      float* cp = d.c + (size_t)m * d.ldc + n;
-      *cp = epilogue(d, v, m, n, cp);
+      if (cols[j] >= d.n) continue;
+      float* cp = d.c + (size_t)rows[i] * d.ldc + cols[j];
+      *cp = epilogue(d, sum[i][j], rows[i], cols[j], cp);
     }
   }
   if (tid == 0) *ticket = 0u;  // self-resetting: the workspace can be reused by the next launch
@@ -204,6 +227,13 @@ bool pipe_ok(const GemmDesc& d) {
 }
 
 }  // namespace
+
+// Zero the ticket block once per C-ABI call; every split-K launch leaves it zeroed again.
+int prepare_gemm_workspace(void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < 65536) return GML_OK;
+  GML_CUDA_TRY(cudaMemsetAsync(ws, 0, 65536, st));
+  return GML_OK;
+}
 
 size_t gemm_workspace_bytes() {
   // Split-K is only used while tiles < 2 * SMs, with splits <= ceil(2 * SMs / tiles): the partial planes
@@ -234,7 +264,8 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   if (splits > nk / 4) splits = nk / 4;  // at least 4 k-tiles per split
   if (splits > 16) splits = 16;
   if (splits < 1) splits = 1;
-  const size_t ticket_bytes = round_up((size_t)tiles * sizeof(unsigned int), 256);
+  const size_t ticket_bytes = 65536;  // fixed-size ticket block at the head of the workspace
+  if ((size_t)tiles * sizeof(unsigned int) > ticket_bytes) return GML_E_UNSUPPORTED;
   while (splits > 1) {
     size_t need = ticket_bytes;
     for (int i = 0; i < count; ++i) need += round_up((size_t)splits * descs[i].m * descs[i].n * sizeof(float), 256);
@@ -253,7 +284,7 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
       pb.part[i] = reinterpret_cast<float*>(p);
       p += round_up((size_t)splits * descs[i].m * descs[i].n * sizeof(float), 256);
     }
-    GML_CUDA_TRY(cudaMemsetAsync(pb.tickets, 0, ticket_bytes, st));
+    // tickets must be zero on entry (prepare_gemm_workspace) and are restored to zero by the kernel
   }
   dim3 grid(tiles_n, tiles_m, count * splits);
   {

@@ -66,10 +66,20 @@ struct GemmDesc {
 // gemm_workspace_bytes() the pipelined split-K kernel (gemm_kernels.cu) is used whenever the operands
 // are 16-byte aligned; otherwise the generic register-staged kernel (fc_kernels.cu).
 size_t gemm_workspace_bytes();
+int prepare_gemm_workspace(void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st, void* ws = nullptr, size_t ws_bytes = 0);
 
-// out[j] = sum_i x[i*ld + j], i < rows, j < cols  (fixed order)
+// out[j] = sum_i x[i*ld + j], i < rows, j < cols  (fixed order); up to 4 independent sums per launch.
+// A segment with run_v != nullptr also applies the running-mean update (balanced_mmtm.py:113-114) to
+// run_v / run_s with its column sums (n_total, step as floats).
+struct ColsumSeg {
+  const float* x; float* out;
+  int rows, cols, ld;
+  float* run_v; float* run_s;
+  float n_total, step;
+};
+int launch_colsums(const ColsumSeg* segs, int count, cudaStream_t st);
 int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st);
 // z rows for mode 3: z[n, off + j] = v[j]
 int launch_fill_rows(float* z, int rows, int ld, int off, const float* v, int cols, cudaStream_t st);
