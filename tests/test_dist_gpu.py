@@ -1,0 +1,140 @@
+"""Data-parallel hot path on 2 GPUs (NCCL): the MMTM block under batch sharding equals the
+single-process block on the concatenated batch, including the global-batch running gate mean and
+the curation modes that depend on it; guided training keeps ranks in lock-step.
+Run with `gpurun --gpus 2`; skipped on a single-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import mmtm_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _entry(fn, rank, world, port, q):
+    import traceback
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    try:
+        from greedy_multimodal_learning_b200 import dist as gdist
+        gdist.init_from_env("nccl")
+        out = fn(rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, True, out))
+    except Exception:
+        q.put((rank, False, traceback.format_exc()))
+
+
+def _spawn(fn, world=2):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_entry, args=(fn, r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+    results = {}
+    while not q.empty():
+        r, ok, payload = q.get()
+        results[r] = (ok, payload)
+    assert len(results) == world, [p.exitcode for p in procs]
+    for r, (ok, payload) in sorted(results.items()):
+        assert ok, "rank %d: %s" % (r, payload)
+    return [results[r][1] for r in range(world)]
+
+
+N, C, H = 6, 32, 8
+SEQ = [0, 1, 0, 2, 0]  # normal, curate visual, normal, curate skeleton, normal
+
+
+def _mmtm_worker(rank, world):
+    import greedy_multimodal_learning_b200 as pkg
+    from greedy_multimodal_learning_b200 import dist as gdist
+    dev = torch.device("cuda", rank)
+    p = mo.synth_params(3, C, C)
+    m = pkg.MMTM_mitigate(C, C, 4)
+    with torch.no_grad():
+        for dst, src in zip((m.fc_squeeze.weight, m.fc_squeeze.bias, m.fc_visual.weight, m.fc_visual.bias,
+                             m.fc_skeleton.weight, m.fc_skeleton.bias), p.tensors()):
+            dst.copy_(src)
+    m.to(dev)
+    lo, hi = gdist.shard_batch(N)  # 3 + 3; uneven split below
+    if rank == 0:
+        lo, hi = 0, 2
+    else:
+        lo, hi = 2, N
+    outs = []
+    for i, mode in enumerate(SEQ):
+        x = mo.synth_inputs(100 + i, N, C, H)
+        kw = {1: dict(curation_mode=True, caring_modality=0), 2: dict(curation_mode=True, caring_modality=1)}.get(mode, {})
+        a = x["A"][lo:hi].to(dev).requires_grad_(True)
+        b = x["B"][lo:hi].to(dev).requires_grad_(True)
+        a_out, b_out, _, _ = m(a, b, **kw)
+        torch.autograd.backward([a_out, b_out], [x["gA"][lo:hi].to(dev), x["gB"][lo:hi].to(dev)])
+        outs.append(dict(A_out=a_out.detach().cpu().numpy(), dA=a.grad.cpu().numpy(), dB=b.grad.cpu().numpy(),
+                         run_v=m.running_avg_weight_visual.cpu().numpy(), lo=lo, hi=hi))
+    return outs
+
+
+def test_mmtm_block_under_batch_sharding_equals_full_batch():
+    res = _spawn(_mmtm_worker)
+    p = mo.synth_params(3, C, C)
+    st = mo.MMTMState.zeros(C)
+    for i, mode in enumerate(SEQ):
+        x = mo.synth_inputs(100 + i, N, C, H)
+        o = mo.forward_backward(x["A"], x["B"], p, st, x["gA"], x["gB"], mode)
+        for rank in range(2):
+            r = res[rank][i]
+            lo, hi = r["lo"], r["hi"]
+            np.testing.assert_allclose(r["A_out"], o["A_out"][lo:hi].numpy(), rtol=2e-5, atol=2e-6)
+            np.testing.assert_allclose(r["dA"], o["dA"][lo:hi].numpy(), rtol=2e-5, atol=2e-6)
+            np.testing.assert_allclose(r["dB"], o["dB"][lo:hi].numpy(), rtol=2e-5, atol=2e-6)
+            np.testing.assert_allclose(r["run_v"], st.run_v.numpy(), rtol=1e-5, atol=1e-7)
+        assert np.array_equal(res[0][i]["run_v"], res[1][i]["run_v"])  # identical on every rank
+
+
+def _train_worker(rank, world):
+    import greedy_multimodal_learning_b200 as pkg
+    from greedy_multimodal_learning_b200 import dist as gdist
+    from tests.golden import make_golden_cases as cases
+    dev = torch.device("cuda", rank)
+    gdist.seed_everything(777)
+    model = pkg.MMTM_MVCNN().to(dev)
+    model, opt, reducer = gdist.setup_model(model, lambda ps: torch.optim.SGD(ps, lr=0.01))
+    cb = pkg.Bias_Mitigation_Strong(0.003, 2, ["net_view_0", "net_view_1"], 1)
+    cb.set_model(model, ignore=False)
+    flags = []
+
+    class Rec(pkg.Callback):
+        def on_batch_end(self, batch, logs):
+            flags.append((logs["curation_mode"], logs["caring_modality"], round(logs["d_BDR"], 12)))
+
+    engine = pkg.Model_(model, opt, pkg.blend_loss, 2, metrics=[pkg.acc], data_parallel=reducer).to(dev)
+    loader = gdist.ShardedBatches(cases.synth_loader(61, 4, 8, 64))
+    engine.train_loop(loader, epochs=2, steps_per_epoch=4, callbacks=[cb, Rec()])
+    w = float(model.net_view_0.fc.weight.double().sum())
+    return flags, w
+
+
+def test_guided_training_ranks_stay_in_lock_step():
+    (f0, w0), (f1, w1) = _spawn(_train_worker)
+    assert f0 == f1            # same statistic, same decisions on every rank, no extra collective
+    assert w0 == w1            # replicas bit-identical after all-reduced updates
+    assert any(c for c, _, _ in f0)
