@@ -220,6 +220,7 @@ extern int g_fused_threads;
 extern long long* g_fused_trace;
 extern int g_fused_kind;
 extern int g_fused_prefetch;
+extern int g_fused_occ;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -231,6 +232,10 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "fused_kind")) {
     if (value < 0 || value > 2) return GML_E_BADARG;
     g_fused_kind = (int)value; return GML_OK;
+  }
+  if (!strcmp(name, "fused_occ")) {
+    if (value != 4 && value != 5) return GML_E_BADARG;
+    g_fused_occ = (int)value; return GML_OK;
   }
   if (!strcmp(name, "fused_prefetch")) { g_fused_prefetch = value ? 1 : 0; return GML_OK; }
   if (!strcmp(name, "fused_trace_ptr")) { g_fused_trace = reinterpret_cast<long long*>(value); return GML_OK; }

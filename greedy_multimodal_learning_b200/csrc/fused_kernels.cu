@@ -39,6 +39,7 @@ namespace gml {
 int g_fused_cluster = 0;   // tunables (gml_set_tunable): 0 = automatic
 int g_fused_threads = 0;
 int g_fused_kind = 0;      // 0 auto, 1 shared-memory resident, 2 L2 resident
+int g_fused_occ = 4;       // L2-resident kernels: CTAs per SM the register budget is compiled for (4: 64 regs, 5: 48)
 int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch on/off (measured: no gain, off)
 long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
@@ -61,6 +62,7 @@ struct FusedCfg {
   size_t data_bytes;
   long long* trace;  // nullptr unless phase tracing is on: [cta < 8][iter < 16][16 stamps]
   int prefetch;      // L2-resident kernels: issue bulk L2 prefetches of the CTA's planes up front
+  int trace_first;   // first CTA of the traced window (L2-resident kernels)
 };
 
 #define GML_STAMP(k)                                                                       \
@@ -614,6 +616,7 @@ bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out
   f.n_groups = (n + f.g - 1) / f.g;
   f.data_bytes = (size_t)f.pl * hw * sizeof(float);
   f.trace = g_fused_trace;
+  f.trace_first = 0;
   f.prefetch = 0;
   const size_t total = f.data_bytes + extras_bytes(f, true);
   if (total > (cs == 4 ? 232448u : 115000u)) return false;
@@ -731,8 +734,8 @@ __device__ __forceinline__ L2Smem l2_carve(unsigned char* p, const FusedCfg& f) 
   return s;
 }
 
-template <int T, int L, int GMAX>
-__global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, const FusedCfg f) {
+template <int T, int L, int GMAX, int OCC>
+__global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, const FusedCfg f) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -750,6 +753,11 @@ __global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, cons
   const int n0 = grp * f.g;
   const int gcount = min(f.g, f.n - n0);
   const int vplanes = gcount * 2 * f.cq;
+  // phase stamps: trace the CTAs of the LAST-launched clusters' neighbours too -> use a mid-grid window
+  const int iter = 0;
+  const bool stamp_me = f.trace && threadIdx.x == 0 && blockIdx.x >= f.trace_first && blockIdx.x < f.trace_first + 8;
+#define GML_STAMP2(k) do { if (stamp_me) f.trace[((size_t)(blockIdx.x - f.trace_first) * 16 + iter) * 16 + (k)] = clock64(); } while (0)
+  GML_STAMP2(0);
 
   // ---- whole slice on its way HBM -> L2 before the first register load is issued ---------------
   if (f.prefetch) {
@@ -780,7 +788,9 @@ __global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, cons
     const float t = group_sum<L>((a0 + a1) + (a2 + a3));
     if (lane == 0) s.psum[p] = t;
   }
+  GML_STAMP2(1);
   cluster.sync();  // also: every CTA of the cluster is running before remote shared memory is touched
+  GML_STAMP2(2);
   for (int p = tid; p < vplanes; p += T) {
     int g, mod, cl;
     plane_coords(f, p, g, mod, cl);
@@ -790,7 +800,8 @@ __global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, cons
     a.z[(size_t)(n0 + g) * 2 * f.c + k] = mean;
   }
   cluster.sync();
-  gemv_rows_r<T, GMAX, 2>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
+  GML_STAMP2(3);
+  gemv_rows<T, GMAX>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
                           2 * f.c, gcount, [&](int r, const float* acc) {
                             const int dd = rank * f.dq + r;
                             const float bias = s.bias_h[r];
@@ -801,8 +812,10 @@ __global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, cons
                               a.h[(size_t)(n0 + g) * f.d + dd] = hval;
                             }
                           });
+  GML_STAMP2(4);
   cluster.sync();
-  gemv_rows_r<T, GMAX, 2>(
+  GML_STAMP2(5);
+  gemv_rows<T, GMAX>(
       [&](int r) {
         return r < f.cq ? a.w_v + (size_t)(rank * f.cq + r) * f.d : a.w_s + (size_t)(rank * f.cq + r - f.cq) * f.d;
       },
@@ -817,7 +830,9 @@ __global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, cons
           gout[(size_t)(n0 + g) * f.c + ch] = gate;
         }
       });
+  GML_STAMP2(6);
   __syncthreads();
+  GML_STAMP2(7);
   // ---- pass 2: re-read (L2), gate, stream out ---------------------------------------------------
   for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
     int g, mod, cl;
@@ -843,11 +858,14 @@ __global__ void __launch_bounds__(T, 4) l2_fwd_kernel(const FusedFwdArgs a, cons
       }
     }
   }
+  GML_STAMP2(8);
+  GML_STAMP2(9);
   // no trailing cluster barrier: remote shared-memory writes only happen before the third barrier
+#undef GML_STAMP2
 }
 
-template <int T, int L, int GMAX>
-__global__ void __launch_bounds__(T, 4) l2_bwd_kernel(const FusedBwdArgs a, const FusedCfg f) {
+template <int T, int L, int GMAX, int OCC>
+__global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, const FusedCfg f) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -1012,7 +1030,8 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
   f.pc = f.pl; f.nchunk = 1;
   f.n_groups = (n + f.g - 1) / f.g;
   f.data_bytes = 0;
-  f.trace = nullptr;
+  f.trace = g_fused_trace;
+  f.trace_first = (f.n_groups / 2) * cs;
   f.prefetch = g_fused_prefetch && ((size_t)hw * 4) % 16 == 0;
   if ((long long)f.n_groups * cs > 0x7fffffffLL) return false;
   *out = f;
@@ -1041,7 +1060,11 @@ int do_launch_l2(K kern, const Args& args, const FusedCfg& f, bool bwd, cudaStre
 template <typename Args>
 int dispatch_l2_fwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
   const int l = lanes_for(f.hw);
-#define GML_L2F(LL, GG) return do_launch_l2(l2_fwd_kernel<256, LL, GG>, args, f, false, st, kTagFusedFwd)
+#define GML_L2F(LL, GG)                                                                              \
+  do {                                                                                               \
+    if (g_fused_occ == 5) return do_launch_l2(l2_fwd_kernel<256, LL, GG, 5>, args, f, false, st, kTagFusedFwd); \
+    return do_launch_l2(l2_fwd_kernel<256, LL, GG, 4>, args, f, false, st, kTagFusedFwd);             \
+  } while (0)
   if (f.g == 1) { if (l == 32) GML_L2F(32, 1); if (l == 16) GML_L2F(16, 1); GML_L2F(8, 1); }
   if (l == 32) GML_L2F(32, 2);
   if (l == 16) GML_L2F(16, 2);
@@ -1051,7 +1074,11 @@ int dispatch_l2_fwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
 template <typename Args>
 int dispatch_l2_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
   const int l = lanes_for(f.hw);
-#define GML_L2B(LL, GG) return do_launch_l2(l2_bwd_kernel<256, LL, GG>, args, f, true, st, kTagFusedBwd)
+#define GML_L2B(LL, GG)                                                                              \
+  do {                                                                                               \
+    if (g_fused_occ == 5) return do_launch_l2(l2_bwd_kernel<256, LL, GG, 5>, args, f, true, st, kTagFusedBwd); \
+    return do_launch_l2(l2_bwd_kernel<256, LL, GG, 4>, args, f, true, st, kTagFusedBwd);              \
+  } while (0)
   if (f.g == 1) { if (l == 32) GML_L2B(32, 1); if (l == 16) GML_L2B(16, 1); GML_L2B(8, 1); }
   if (l == 32) GML_L2B(32, 2);
   if (l == 16) GML_L2B(16, 2);

@@ -13,16 +13,21 @@ from greedy_multimodal_learning_b200 import _lib as L  # noqa: E402
 lib = L.load()
 dev = torch.device("cuda:0")
 NAMES = ["pass1", "sync", "scatter+csync", "fc1", "csync", "fc2", "sync", "pass2", "sync"]
-for (c, h, n) in ((128, 28, 256), (256, 14, 256)):
-    for cs, thr in ((4, 512), (8, 256)):
-        L.check(lib.gml_set_tunable(b"fused_kind", 1))
+KIND = int(os.environ.get("TRACE_KIND", "1"))
+for (c, h, n) in ((128, 28, int(os.environ.get("TRACE_N", "256"))), (256, 14, int(os.environ.get("TRACE_N", "256")))):
+    for cs, thr in (((4, 512), (8, 256)) if KIND == 1 else ((8, 0), (4, 0))):
+        L.check(lib.gml_set_tunable(b"fused_kind", KIND))
         L.check(lib.gml_set_tunable(b"fused_cluster", cs))
         L.check(lib.gml_set_tunable(b"fused_threads", thr))
         b = BlockBuffers(torch, L, n, c, h, dev, seed=c)
         st = torch.cuda.current_stream().cuda_stream
         for what in ("fwd", "bwd"):
             trace = torch.zeros(8 * 16 * 16, dtype=torch.int64, device=dev)
-            b.fwd_bwd(lib, L, st, L.F_FORCE_FUSED)  # warm
+            try:
+                b.fwd_bwd(lib, L, st, L.F_FORCE_FUSED)  # warm
+            except L.GmlError:
+                print("== C=%d cs=%d unsupported" % (c, cs))
+                break
             torch.cuda.synchronize()
             L.check(lib.gml_set_tunable(b"fused_trace_ptr", trace.data_ptr()))
             if what == "fwd":
@@ -46,8 +51,8 @@ for (c, h, n) in ((128, 28, 256), (256, 14, 256)):
             L.check(lib.gml_set_tunable(b"fused_trace_ptr", 0))
             t = trace.cpu().view(8, 16, 16).numpy()
             print("== C=%d H=%d N=%d cs=%d T=%d %s (cycles; CTA 0 and CTA 5)" % (c, h, n, cs, thr, what))
-            for cta in (0, 5):
-                for it in range(8):
+            for cta in ((0, 5) if KIND == 1 else (0, 1, 2, 5)):
+                for it in range(8 if KIND == 1 else 1):
                     row = t[cta, it]
                     if row[0] == 0:
                         break
