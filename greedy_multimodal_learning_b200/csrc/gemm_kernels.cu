@@ -17,10 +17,14 @@ namespace gml {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, STAGES = 3, THREADS = 256;
+// Two tile shapes share one kernel template: 64x64 (4x4 outputs per thread, static shared memory) for the
+// small problems and 128x128 (8x8 per thread, 60 KB dynamic shared memory) for batch >= 512.
+constexpr int BK = 16, STAGES = 3, THREADS = 256;
 constexpr int PITCH_KC = BK + 4;   // [row][k] rows of 16 floats, pitch 20 -> conflict-free 128-bit reads
-constexpr int PITCH_MN = BM + 4;   // [k][row] rows of 64 floats, pitch 68
-constexpr int TILE_FLOATS = (BM * PITCH_KC > BK * PITCH_MN) ? BM * PITCH_KC : BK * PITCH_MN;  // 1280
+template <int BT> struct TileGeom {
+  static constexpr int kPitchMN = BT + 4;  // [k][row]
+  static constexpr int kFloats = (BT * PITCH_KC > BK * (BT + 4)) ? BT * PITCH_KC : BK * (BT + 4);
+};
 
 struct PipeBatch {
   GemmDesc d[2];
@@ -39,41 +43,53 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // one operand tile for k in [k0, k0 + BK): KC = k-contiguous source (src[t * ld + k]), else src[k * ld + t]
-template <bool KC>
+template <bool KC, int BT>
 __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ src, int ld, int t0, int tmax, int k0,
                                           int kmax, int tid) {
-  if (KC) {
-    const int row = tid >> 2, kc = (tid & 3) * 4;
-    const int t = t0 + row, k = k0 + kc;
-    int bytes = (t < tmax) ? (kmax - k) * 4 : 0;
-    bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-    const float* g = bytes > 0 ? src + (size_t)t * ld + k : src;
-    cp_async16(s + row * PITCH_KC + kc, g, bytes);
-  } else {
-    const int kk = tid >> 4, tq = (tid & 15) * 4;
-    const int k = k0 + kk, t = t0 + tq;
-    int bytes = (k < kmax) ? (tmax - t) * 4 : 0;
-    bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-    const float* g = bytes > 0 ? src + (size_t)k * ld + t : src;
-    cp_async16(s + kk * PITCH_MN + tq, g, bytes);
+  constexpr int kChunks = BT * BK / 4;  // 16-byte chunks per tile
+#pragma unroll
+  for (int c = tid; c < kChunks; c += THREADS) {
+    if (KC) {
+      const int row = c >> 2, kc = (c & 3) * 4;
+      const int t = t0 + row, k = k0 + kc;
+      int bytes = (t < tmax) ? (kmax - k) * 4 : 0;
+      bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+      const float* g = bytes > 0 ? src + (size_t)t * ld + k : src;
+      cp_async16(s + row * PITCH_KC + kc, g, bytes);
+    } else {
+      const int kk = c / (BT / 4), tq = (c % (BT / 4)) * 4;
+      const int k = k0 + kk, t = t0 + tq;
+      int bytes = (k < kmax) ? (tmax - t) * 4 : 0;
+      bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+      const float* g = bytes > 0 ? src + (size_t)k * ld + t : src;
+      cp_async16(s + kk * TileGeom<BT>::kPitchMN + tq, g, bytes);
+    }
   }
 }
 
-// 4 (rows of this thread) x 4 (k) block of an operand tile
-template <bool KC>
-__device__ __forceinline__ void frag(const float* s, int t_idx, int kk, float (&v)[4][4]) {
+// row of the tile that output slot i of thread-coordinate t_idx maps to
+template <bool KC, int TM>
+__device__ __forceinline__ int tile_row(int t_idx, int i) {
+  return KC ? t_idx + 16 * i : (i >> 2) * 64 + t_idx * 4 + (i & 3);
+}
+// TM (rows of this thread) x 4 (k) block of an operand tile
+template <bool KC, int TM>
+__device__ __forceinline__ void frag(const float* s, int t_idx, int kk, float (&v)[TM][4]) {
   if (KC) {  // rows t_idx + 16 i, vector along k
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM; ++i) {
       const float4 t = *reinterpret_cast<const float4*>(s + (t_idx + 16 * i) * PITCH_KC + kk);
       v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
     }
-  } else {   // rows 4 t_idx + i, vector along rows
+  } else {   // rows (h * 64 + 4 t_idx + i), vector along rows
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 t = *reinterpret_cast<const float4*>(s + (kk + q) * PITCH_MN + t_idx * 4);
-      v[0][q] = t.x; v[1][q] = t.y; v[2][q] = t.z; v[3][q] = t.w;
-    }
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int h = 0; h < TM / 4; ++h) {
+        const float4 t =
+            *reinterpret_cast<const float4*>(s + (kk + q) * TileGeom<16 * TM>::kPitchMN + h * 64 + t_idx * 4);
+        v[h * 4 + 0][q] = t.x; v[h * 4 + 1][q] = t.y; v[h * 4 + 2][q] = t.z; v[h * 4 + 3][q] = t.w;
+      }
   }
 }
 
@@ -86,10 +102,13 @@ __device__ __forceinline__ float epilogue(const GemmDesc& d, float v, int m, int
   return v;
 }
 
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(THREADS) gemm_pipe_kernel(const PipeBatch pb) {
-  __shared__ __align__(16) float As[STAGES][TILE_FLOATS];
-  __shared__ __align__(16) float Bs[STAGES][TILE_FLOATS];
+template <bool A_KC, bool B_KC, int TM>
+__global__ void __launch_bounds__(THREADS, TM == 4 ? 2 : 1) gemm_pipe_kernel(const PipeBatch pb) {
+  constexpr int BM = 16 * TM, BN = 16 * TM;
+  constexpr int TILE_FLOATS = TileGeom<BM>::kFloats;
+  extern __shared__ __align__(16) float gemm_smem[];
+  float (*As)[TILE_FLOATS] = reinterpret_cast<float (*)[TILE_FLOATS]>(gemm_smem);
+  float (*Bs)[TILE_FLOATS] = reinterpret_cast<float (*)[TILE_FLOATS]>(gemm_smem + STAGES * TILE_FLOATS);
   __shared__ unsigned int s_ticket;
   const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
   const GemmDesc d = prob ? pb.d[1] : pb.d[0];
@@ -100,17 +119,17 @@ __global__ void __launch_bounds__(THREADS) gemm_pipe_kernel(const PipeBatch pb) 
   const int k_end = min(d.k, k_begin + pb.k_per_split);
   const int nk = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
 
-  float acc[4][4];
+  float acc[TM][TM];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_tile<A_KC>(As[s], d.a, d.lda, m0, d.m, k_begin + s * BK, k_end, tid);
-      load_tile<B_KC>(Bs[s], d.b, d.ldb, n0, d.n, k_begin + s * BK, k_end, tid);
+      load_tile<A_KC, BM>(As[s], d.a, d.lda, m0, d.m, k_begin + s * BK, k_end, tid);
+      load_tile<B_KC, BN>(Bs[s], d.b, d.ldb, n0, d.n, k_begin + s * BK, k_end, tid);
     }
     cp_async_commit();
   }
@@ -119,37 +138,37 @@ __global__ void __launch_bounds__(THREADS) gemm_pipe_kernel(const PipeBatch pb) 
     __syncthreads();
     const int nxt = kt + STAGES - 1;
     if (nxt < nk) {
-      load_tile<A_KC>(As[nxt % STAGES], d.a, d.lda, m0, d.m, k_begin + nxt * BK, k_end, tid);
-      load_tile<B_KC>(Bs[nxt % STAGES], d.b, d.ldb, n0, d.n, k_begin + nxt * BK, k_end, tid);
+      load_tile<A_KC, BM>(As[nxt % STAGES], d.a, d.lda, m0, d.m, k_begin + nxt * BK, k_end, tid);
+      load_tile<B_KC, BN>(Bs[nxt % STAGES], d.b, d.ldb, n0, d.n, k_begin + nxt * BK, k_end, tid);
     }
     cp_async_commit();
     const float* as = As[kt % STAGES];
     const float* bs = Bs[kt % STAGES];
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      float av[4][4], bv[4][4];
-      frag<A_KC>(as, ty, kk, av);
-      frag<B_KC>(bs, tx, kk, bv);
+      float av[TM][4], bv[TM][4];
+      frag<A_KC, TM>(as, ty, kk, av);
+      frag<B_KC, TM>(bs, tx, kk, bv);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i][q], bv[j][q], acc[i][j]);
+          for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(av[i][q], bv[j][q], acc[i][j]);
     }
   }
   cp_async_wait<0>();
 
-  auto row_of = [&](int i) { return m0 + (A_KC ? ty + 16 * i : ty * 4 + i); };
-  auto col_of = [&](int j) { return n0 + (B_KC ? tx + 16 * j : tx * 4 + j); };
+  auto row_of = [&](int i) { return m0 + tile_row<A_KC, TM>(ty, i); };
+  auto col_of = [&](int j) { return n0 + tile_row<B_KC, TM>(tx, j); };
 
   if (pb.splits == 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM; ++i) {
       const int m = row_of(i);
       if (m >= d.m) continue;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < TM; ++j) {
         const int n = col_of(j);
         if (n >= d.n) continue;
         float* cp = d.c + (size_t)m * d.ldc + n;
@@ -162,11 +181,11 @@ __global__ void __launch_bounds__(THREADS) gemm_pipe_kernel(const PipeBatch pb) 
   float* part = pb.part[prob];
   const size_t plane = (size_t)d.m * d.n;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < TM; ++i) {
     const int m = row_of(i);
     if (m >= d.m) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < TM; ++j) {
       const int n = col_of(j);
       if (n < d.n) __stcg(part + (size_t)split * plane + (size_t)m * d.n + n, acc[i][j]);
     }
@@ -180,36 +199,36 @@ __global__ void __launch_bounds__(THREADS) gemm_pipe_kernel(const PipeBatch pb) 
   __threadfence();
   // fold the partials in split order; all 16 loads of a split are issued together (L2 latency, not
   // bandwidth, is the cost here), splits unrolled by two
-  float sum[4][4];
+  float sum[TM][TM];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sum[i][j] = 0.f;
-  int rows[4], cols[4];
+    for (int j = 0; j < TM; ++j) sum[i][j] = 0.f;
+  int rows[TM], cols[TM];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { rows[i] = row_of(i); cols[i] = col_of(i); }
+  for (int i = 0; i < TM; ++i) { rows[i] = row_of(i); cols[i] = col_of(i); }
   for (int s0 = 0; s0 < pb.splits; s0 += 2) {
-    float v0[4][4], v1[4][4];
+    float v0[TM][TM], v1[TM][TM];
     const bool two = s0 + 1 < pb.splits;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < TM; ++j) {
         const bool ok = rows[i] < d.m && cols[j] < d.n;
         const size_t o = (size_t)rows[i] * d.n + cols[j];
         v0[i][j] = ok ? __ldcg(part + (size_t)s0 * plane + o) : 0.f;
         v1[i][j] = (ok && two) ? __ldcg(part + (size_t)(s0 + 1) * plane + o) : 0.f;
       }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) sum[i][j] = (sum[i][j] + v0[i][j]) + v1[i][j];
+      for (int j = 0; j < TM; ++j) sum[i][j] = (sum[i][j] + v0[i][j]) + v1[i][j];
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < TM; ++i) {
     if (rows[i] >= d.m) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < TM; ++j) {
       if (cols[j] >= d.n) continue;
       float* cp = d.c + (size_t)rows[i] * d.ldc + cols[j];
       *cp = epilogue(d, sum[i][j], rows[i], cols[j], cp);
@@ -238,7 +257,7 @@ int prepare_gemm_workspace(void* ws, size_t ws_bytes, cudaStream_t st) {
 size_t gemm_workspace_bytes() {
   // Split-K is only used while tiles < 2 * SMs, with splits <= ceil(2 * SMs / tiles): the partial planes
   // never exceed (2 * SMs + tiles) tiles of 64 x 64 floats, i.e. < 4 * SMs tiles; plus the ticket block.
-  return (size_t)4 * kNumSMs * BM * BN * sizeof(float) + 65536 + 1024;
+  return (size_t)4 * kNumSMs * 128 * 64 * sizeof(float) + 65536 + 1024;
 }
 
 // returns GML_E_UNSUPPORTED when the problems do not meet the pipeline's alignment rules
@@ -257,6 +276,9 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   }
   if (count == 1) pb.d[1] = descs[0];
   if (count == 2 && descs[0].k != descs[1].k) return GML_E_UNSUPPORTED;
+  // big tiles once the batch is large enough to fill the machine with them
+  const bool big = (long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * count >= 24 && min_k >= 64;
+  const int BM = big ? 128 : 64, BN = BM;
   const int tiles_m = ceil_div(max_m, BM), tiles_n = ceil_div(max_n, BN);
   const long tiles = (long)tiles_m * tiles_n * count;
   const int nk = ceil_div(min_k, BK);
@@ -290,10 +312,23 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   {
     LaunchScope ls(kTagGemm, st);
     const bool akc = descs[0].a_kc != 0, bkc = descs[0].b_kc != 0;
-    if (akc && bkc) gemm_pipe_kernel<true, true><<<grid, THREADS, 0, st>>>(pb);
-    else if (akc && !bkc) gemm_pipe_kernel<true, false><<<grid, THREADS, 0, st>>>(pb);
-    else if (!akc && bkc) gemm_pipe_kernel<false, true><<<grid, THREADS, 0, st>>>(pb);
-    else gemm_pipe_kernel<false, false><<<grid, THREADS, 0, st>>>(pb);
+#define GML_GEMM(AK, BKC)                                                                                   \
+  do {                                                                                                      \
+    if (big) {                                                                                              \
+      const size_t sm = 2 * STAGES * TileGeom<128>::kFloats * sizeof(float);                                 \
+      GML_CUDA_TRY(cudaFuncSetAttribute(gemm_pipe_kernel<AK, BKC, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)sm));                                                           \
+      gemm_pipe_kernel<AK, BKC, 8><<<grid, THREADS, sm, st>>>(pb);                                           \
+    } else {                                                                                                \
+      const size_t sm = 2 * STAGES * TileGeom<64>::kFloats * sizeof(float);                                  \
+      gemm_pipe_kernel<AK, BKC, 4><<<grid, THREADS, sm, st>>>(pb);                                           \
+    }                                                                                                       \
+  } while (0)
+    if (akc && bkc) GML_GEMM(true, true);
+    else if (akc && !bkc) GML_GEMM(true, false);
+    else if (!akc && bkc) GML_GEMM(false, true);
+    else GML_GEMM(false, false);
+#undef GML_GEMM
   }
   GML_LAUNCH_CHECK();
   return GML_OK;

@@ -135,7 +135,8 @@ def test_reference_golden_state_sequence(path):
 # modality, N = 1, N that is not a multiple of any tile
 ODD = [(1, 3, 5, 1, 1, 1, 1), (5, 7, 7, 3, 3, 2, 5), (3, 20, 12, 7, 7, 5, 5), (9, 32, 32, 10, 5, 10, 5),
        (2, 6, 10, 4, 4, 9, 9), (33, 64, 64, 13, 13, 13, 13), (4, 128, 128, 28, 28, 28, 28),
-       (130, 24, 24, 6, 6, 6, 6)]
+       (130, 24, 24, 6, 6, 6, 6),
+       (1100, 512, 512, 1, 1, 1, 1)]  # large batch, tiny planes: the 128x128-tile split-K GEMMs in every layout
 
 
 @pytest.mark.parametrize("path", list(PATHS))
