@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 One "step" = one forward+backward of the three MMTM blocks of the 2-view ResNet-18
-(128x28^2, 256x14^2, 512x7^2) at batch 256 per GPU, fp32 -- the MMTM work of one
-`training_guided.gin` step at batch 256 (BASELINE.json configs[1] at the batch of configs[2]).
+(128x28^2, 256x14^2, 512x7^2) at batch 1024 per GPU, fp32 -- the top of BASELINE.json configs[1]
+("MMTM fwd/bwd microbench sweep ... batch 32-1024, single B200"), i.e. the steady-state regime; the
+`sweep` key repeats the measurement at batch 32 and 256 (256 = the `training_guided.gin` batch of
+configs[2], which the `train` key times end to end).
 Prints ONE JSON line (rank 0):
 
   value      algorithmic GB/s (40*N*C*HW bytes per block) over all ranks, inputs
@@ -227,7 +229,7 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "MMTM fwd+bwd, blocks 128x28^2+256x14^2+512x7^2, CPU reference path (oracle port), "
-                                  "bounded sample batch 32 of the batch-256 workload"},
+                                  "bounded sample batch 32 of the batch-1024 workload"},
            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -289,6 +291,26 @@ def run_ours(args):
                 graph.replay()
             torch.cuda.synchronize()
     ms = max_over_ranks(ms)
+    # ---- the rest of the configs[1] sweep (same protocol, fewer replays) ------------------------------
+    sweep = {}
+    for nb in (32, 256):
+        if nb == n:
+            continue
+        sb = [BlockBuffers(torch, L, nb, c, h, dev, seed=c + rank) for c, h in SHAPES]
+        with torch.cuda.stream(stream):
+            for b_ in sb:
+                b_.fwd_bwd(lib, L, stream.cuda_stream, flags)
+            stream.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=stream):
+                for b_ in sb:
+                    b_.fwd_bwd(lib, L, stream.cuda_stream, flags)
+            ms_b = max_over_ranks(time_events(torch, g2.replay, max(args.steps, 10), 3, sync_ranks))
+        sweep["batch_%d" % nb] = {"ms_per_step": ms_b, "value": step_bytes(nb) * world / (ms_b * 1e-3) / 1e9,
+                                  "unit": UNIT, "frac_of_measured_hbm_peak": step_bytes(nb) / (ms_b * 1e-3) / 1e9 /
+                                  measured_peak()[0]}
+        del g2, sb
+        torch.cuda.empty_cache()
     u_total = sum(n * c * h * h * 4 for c, h in SHAPES)  # one modality, all three blocks
     total_bytes = step_bytes(n) * world
     value = total_bytes / (ms * 1e-3) / 1e9
@@ -386,7 +408,7 @@ def run_ours(args):
                "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "launches_per_step":
                int(launches_per_step), "e2e": e2e, "roofline": roof, "kernels": kernels,
                "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-               "frac_of_measured_hbm_peak": value / world / peak, "train": train}
+               "frac_of_measured_hbm_peak": value / world / peak, "sweep": sweep, "train": train}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -438,7 +460,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="MMTM batch per GPU")
+    ap.add_argument("--batch", type=int, default=1024, help="MMTM batch per GPU")
     ap.add_argument("--train-batch", type=int, default=256, help="training batch per GPU")
     ap.add_argument("--path", default="auto", choices=["auto", "streaming", "fused"])
     ap.add_argument("--no-train", action="store_true")

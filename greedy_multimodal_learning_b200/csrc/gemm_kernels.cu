@@ -15,6 +15,8 @@
 
 namespace gml {
 
+int g_gemm_big_tiles = 0;  // tunable "gemm_big_tiles"
+
 namespace {
 
 // Two tile shapes share one kernel template: 64x64 (4x4 outputs per thread, static shared memory) for the
@@ -276,8 +278,9 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   }
   if (count == 1) pb.d[1] = descs[0];
   if (count == 2 && descs[0].k != descs[1].k) return GML_E_UNSUPPORTED;
-  // big tiles once the batch is large enough to fill the machine with them
-  const bool big = (long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * count >= 24 && min_k >= 64;
+  // 128x128 tiles (8x8 outputs per thread, 1 CTA per SM at ~250 registers) measured SLOWER than 64x64 at
+  // 2 CTAs per SM on every FC shape of the three blocks (profiles/), so they are opt-in only.
+  const bool big = g_gemm_big_tiles && (long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * count >= 24 && min_k >= 64;
   const int BM = big ? 128 : 64, BN = BM;
   const int tiles_m = ceil_div(max_m, BM), tiles_n = ceil_div(max_n, BN);
   const long tiles = (long)tiles_m * tiles_n * count;

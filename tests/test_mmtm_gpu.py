@@ -144,6 +144,8 @@ ODD = [(1, 3, 5, 1, 1, 1, 1), (5, 7, 7, 3, 3, 2, 5), (3, 20, 12, 7, 7, 5, 5), (9
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_oracle_parity_odd_shapes(shape, mode, path):
     n, c_v, c_s, h_v, w_v, h_s, w_s = shape
+    # the large-batch case also exercises the opt-in 128x128-tile GEMM
+    _lib.check(_lib.load().gml_set_tunable(b"gemm_big_tiles", 1 if n > 1000 and path == "auto" else 0))
     if mode == 2 and c_v != c_s:
         pytest.skip("reference cannot substitute the skeleton gate when dims differ (balanced_mmtm.py:31)")
     rs = np.random.RandomState(n * 1000 + c_v)
@@ -161,6 +163,7 @@ def test_oracle_parity_odd_shapes(shape, mode, path):
     for k in ["A_out", "B_out", "dA", "dB", "gA", "gB", "dWsq", "dbsq", "dWv", "dbv", "dWs", "dbs"]:
         assert_close(r[k], o[k], 1e-5, k)
     assert_close(r["run_v"], st.run_v, 1e-6, "run_v")
+    _lib.check(_lib.load().gml_set_tunable(b"gemm_big_tiles", 0))
 
 
 # shapes the cluster / shared-memory-resident kernels accept (forced: GML_F_FORCE_FUSED fails loudly
