@@ -193,6 +193,7 @@ def cpu_baseline_train(torch, batch=8, iters=3):
     import greedy_multimodal_learning_b200 as pkg
     from oracle.mmtm_module import OracleMMTM
     from oracle import stats_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(777)
     model = pkg.MMTM_MVCNN(mmtm_cls=OracleMMTM)
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
@@ -232,7 +233,7 @@ def run_reference(args):
                                   "bounded sample batch 32 of the batch-1024 workload"},
            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def run_ours(args):
@@ -392,8 +393,9 @@ def run_ours(args):
 
     out = None
     if rank == 0:
-        cpu = cpu_baseline_mmtm(torch)
-        if train is not None and not args.no_cpu_train:
+        # CPU baselines are a single-process, N=1 measurement (torchrun pins OMP threads for N>1)
+        cpu = cpu_baseline_mmtm(torch) if world == 1 else None
+        if train is not None and not args.no_cpu_train and world == 1:
             train["cpu_reference"] = cpu_baseline_train(torch)
             train["speedup_vs_cpu_reference"] = train["samples_per_s"] / train["cpu_reference"]["samples_per_s"]
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -407,9 +409,9 @@ def run_ours(args):
                           "kernel_path": args.path, "launch": "CUDA graph replay of the C-ABI calls"},
                "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "launches_per_step":
                int(launches_per_step), "e2e": e2e, "roofline": roof, "kernels": kernels,
-               "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+               "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
                "frac_of_measured_hbm_peak": value / world / peak, "sweep": sweep, "train": train}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -454,7 +456,25 @@ def bench_train(torch, pkg, gdist, dev, world, rank, args, sync_ranks, max_over_
             "curation_mode_at_end": bool(engine.curation_mode)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything libraries print (e.g. NCCL's version banner)
+    was redirected to stderr in main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -24,17 +24,27 @@ def _free_port():
 def _spawn(fn, world=2):
     port = _free_port()
     ctx = mp.get_context("spawn")
-    q = ctx.SimpleQueue()
+    q = ctx.Queue()
     procs = [ctx.Process(target=_entry, args=(fn, r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(180)
+    # drain the queue BEFORE joining: a child blocks in put() until its (possibly large) result is read
     results = {}
-    while not q.empty():
-        r, ok, payload = q.get()
-        results[r] = (ok, payload)
-    assert len(results) == world, "a rank died: %s" % ([p.exitcode for p in procs],)
+    import queue as _queue
+    import time as _time
+    deadline = _time.time() + 170
+    while len(results) < world and _time.time() < deadline:
+        try:
+            r, ok, payload = q.get(timeout=1.0)
+            results[r] = (ok, payload)
+        except _queue.Empty:
+            if all(not p.is_alive() for p in procs) and q.empty():
+                break
+    for p in procs:
+        p.join(30)
+        if p.is_alive():
+            p.kill()
+    assert len(results) == world, "a rank died or hung: %s" % ([p.exitcode for p in procs],)
     for r, (ok, payload) in sorted(results.items()):
         assert ok, "rank %d: %s" % (r, payload)
     return [results[r][1] for r in range(world)]
