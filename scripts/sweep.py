@@ -20,6 +20,7 @@ from greedy_multimodal_learning_b200 import _lib as L  # noqa: E402
 
 VARIANTS = {
     # name: (flags, tunables)
+    "auto": (0, {}),
     "stream_c40": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 40}),
     "stream_c64": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 64}),
     "stream_c100": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 100}),
