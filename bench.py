@@ -350,10 +350,14 @@ def run_ours(args):
                 kernels[key] = entry
     peak, peak_src = measured_peak()
     roof = None
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if dominant and os.path.isfile(tfile):  # dram bytes per launch from the committed ncu --set full capture
+        traffic = json.load(open(tfile)).get("%s@%d" % (dominant, n), {}).get("traffic_bytes_per_launch")
     if dominant:
         k = kernels[dominant]
         roof = {"bound": "hbm", "kernel": dominant, "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": k["algorithmic_gbs"] / peak, "traffic": None, "peak_source": peak_src + ", burst copy",
+                "frac": k["algorithmic_gbs"] / peak, "traffic": traffic, "peak_source": peak_src + ", burst copy",
                 "algorithmic_bytes_per_launch": k["algorithmic_bytes_per_launch"],
                 "avg_launch_ms": k["ms_per_step"] / k["launches_per_step"],
                 "share_of_step": k["ms_per_step"] / step_prof_ms, "whole_step_frac": value / world / peak,
