@@ -98,6 +98,11 @@ __device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t policy) {
                : "l"(p), "l"(policy));
   return r;
 }
+__device__ __forceinline__ float ldg_hint_f32(const float* p, uint64_t policy) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(policy));
+  return r;
+}
 // streaming store: written once, not re-read by this kernel
 __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),

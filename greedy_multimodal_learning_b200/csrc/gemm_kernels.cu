@@ -105,7 +105,7 @@ __device__ __forceinline__ float epilogue(const GemmDesc& d, float v, int m, int
 }
 
 template <bool A_KC, bool B_KC, int TM>
-__global__ void __launch_bounds__(THREADS, TM == 4 ? 2 : 1) gemm_pipe_kernel(const PipeBatch pb) {
+__global__ void __launch_bounds__(THREADS, TM == 4 ? 3 : 1) gemm_pipe_kernel(const PipeBatch pb) {
   constexpr int BM = 16 * TM, BN = 16 * TM;
   constexpr int TILE_FLOATS = TileGeom<BM>::kFloats;
   extern __shared__ __align__(16) float gemm_smem[];

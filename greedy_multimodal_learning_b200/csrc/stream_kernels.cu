@@ -73,21 +73,27 @@ __global__ void __launch_bounds__(kThreads) plane_reduce_kernel(ReduceLaunch p) 
       }
       acc = (a0 + a1) + (a2 + a3);
     } else {
+      // planes that are not 16-byte tileable (HW = 49): scalar loads, 8 independent ones in flight per lane
       const float* x = s.x + base;
       const float* y = DUAL ? s.y + base : nullptr;
+      const uint64_t pol = p.keep_in_l2 ? policy_evict_last() : policy_evict_first();
       float a0 = 0.f, a1 = 0.f;
-      int j = lane;
-      for (; j + L < hw; j += 2 * L) {
-        float x0 = __ldg(x + j), x1 = __ldg(x + j + L);
-        if constexpr (DUAL) {
-          a0 = fmaf(x0, __ldg(y + j), a0); a1 = fmaf(x1, __ldg(y + j + L), a1);
-        } else {
-          a0 += x0; a1 += x1;
+      for (int j0 = lane; j0 < hw; j0 += 8 * L) {
+        float xv[8], yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + u * L;
+          xv[u] = j < hw ? ldg_hint_f32(x + j, pol) : 0.f;
+          if constexpr (DUAL) yv[u] = j < hw ? __ldg(y + j) : 0.f;
         }
-      }
-      if (j < hw) {
-        if constexpr (DUAL) a0 = fmaf(__ldg(x + j), __ldg(y + j), a0);
-        else a0 += __ldg(x + j);
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          if constexpr (DUAL) {
+            a0 = fmaf(xv[u], yv[u], a0); a1 = fmaf(xv[u + 1], yv[u + 1], a1);
+          } else {
+            a0 += xv[u]; a1 += xv[u + 1];
+          }
+        }
       }
       acc = a0 + a1;
     }
@@ -147,7 +153,20 @@ __global__ void __launch_bounds__(kThreads) plane_scale_kernel(ScaleLaunch p) {
   } else {
     const float* x = s.x + base;
     float* o = s.out + base;
-    for (int j = lane; j < hw; j += L) o[j] = fmaf(__ldg(x + j), sc, ad);
+    const uint64_t pol = policy_evict_first();
+    for (int j0 = lane; j0 < hw; j0 += 8 * L) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * L;
+        v[u] = j < hw ? ldg_hint_f32(x + j, pol) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * L;
+        if (j < hw) o[j] = fmaf(v[u], sc, ad);
+      }
+    }
   }
 }
 
