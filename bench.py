@@ -443,10 +443,19 @@ def bench_train(torch, pkg, gdist, dev, world, rank, args, sync_ranks, max_over_
     model.train(True)
     state = {"i": 0}
 
+    def endless():
+        while True:
+            yield None, x, y
+
+    # every step's batch is copied host->device from pinned memory inside the timed region; the copy of
+    # batch i+1 runs on a side stream under the compute of batch i (DevicePrefetcher)
+    batches = iter(pkg.DevicePrefetcher(endless(), dev))
+
     def step():
         state["i"] += 1
         s = {"number": state["i"], "indices": None}
-        engine.train_step(s, x, y, cbs)   # H2D of the batch + loss/accuracy read-back inside
+        _, xd, yd = next(batches)
+        engine.train_step(s, xd, yd, cbs)  # loss/accuracy read-back inside
 
     steps = max(3, min(args.steps, 8))
     ms = max_over_ranks(time_events(torch, step, steps, 3, sync_ranks))
@@ -455,7 +464,8 @@ def bench_train(torch, pkg, gdist, dev, world, rank, args, sync_ranks, max_over_
     roofline_sps = peak * 1e9 / 7_024_640 * world
     return {"samples_per_s": sps, "ms_per_step": ms, "global_batch": bsz * world, "steps": steps,
             "config": "training_guided.gin: 2-view ResNet-18 + MMTM, 224x224, SGD lr 0.1, Bias_Mitigation_Strong "
-                      "eps 0.01 window 5, fp32 (cuDNN TF32 default on), H2D of the batch and loss/acc read-back timed",
+                      "eps 0.01 window 5, fp32 (cuDNN TF32 default on), per-step H2D of the batch (prefetched one step ahead) "
+                      "and loss/acc read-back timed",
             "frac_of_mmtm_memory_roofline": sps / roofline_sps,
             "curation_mode_at_end": bool(engine.curation_mode)}
 

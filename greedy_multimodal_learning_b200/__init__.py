@@ -13,7 +13,7 @@ library is loaded on first use and there is no CPU fallback.
 from ._lib import GmlError, LIB_PATH, load as load_library  # noqa: F401
 from .balanced_mmtm import MMTM_mitigate, SqueezeMeanRecorder, get_mmtm_outputs, get_rescale_weights  # noqa: F401
 from .callbacks import Bias_Mitigation_Random, Bias_Mitigation_Strong, Callback, MultiTensorSqnorm  # noqa: F401
-from .framework import CallbackList, Model_, StepIterator, acc, blend_loss  # noqa: F401
+from .framework import CallbackList, DevicePrefetcher, Model_, StepIterator, acc, blend_loss  # noqa: F401
 from .model import MMTM_MVCNN  # noqa: F401
 
 __version__ = "0.1.0"

@@ -149,6 +149,50 @@ class _Silent(Callback):
     pass
 
 
+class DevicePrefetcher:
+    """Input pipeline for the step engine: wraps a loader of `(idx, data, label)` batches and
+    keeps ONE batch ahead on the device -- the host->device copy of batch i+1 (from pinned memory, on a side
+    stream) overlaps the compute of batch i.  Tuple layout and order are unchanged (dataset.py:116-128)."""
+
+    def __init__(self, loader, device, pin=True):
+        self.loader, self.device, self.pin = loader, torch.device(device), pin
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, batch):
+        idx, data, label = batch
+        conv = lambda t: torch.from_numpy(t) if isinstance(t, np.ndarray) else t
+        data, label = conv(data), conv(label)
+        if self.pin and not data.is_cuda and not data.is_pinned():
+            data, label = data.pin_memory(), label.pin_memory()
+        with torch.cuda.stream(self.stream):
+            d = data.to(self.device, non_blocking=True)
+            l = label.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return idx, d, l, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            idx, d, l, ev = nxt
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            d.record_stream(cur)
+            l.record_stream(cur)
+            try:
+                nxt = self._stage(next(it))
+            except StopIteration:
+                nxt = None
+            yield idx, d, l
+
+
 class Model_:
     """Train / eval loops; reference src/framework.py:125-345.
 

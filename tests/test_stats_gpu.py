@@ -282,3 +282,11 @@ def test_guided_training_trace_on_gpu():
             assert a["acc"] == b["acc"] and a["acc_modal_0"] == b["acc0"] and a["acc_modal_1"] == b["acc1"]
             assert abs(a["loss"] - b["loss"]) <= 5e-3 * abs(b["loss"]), (a["loss"], b["loss"])
             assert abs(a["d_BDR"] - b["d_BDR"]) <= 3e-4, (a["d_BDR"], b["d_BDR"])
+
+
+def test_device_prefetcher_preserves_order_and_values():
+    loader = cases.synth_loader(5, 4, 3, 16)
+    got = list(pkg.DevicePrefetcher(loader, DEV))
+    assert len(got) == len(loader)
+    for (i0, x0, y0), (i1, x1, y1) in zip(loader, got):
+        assert torch.equal(i0, i1) and x1.is_cuda and torch.equal(x0, x1.cpu()) and torch.equal(y0, y1.cpu())
