@@ -222,6 +222,7 @@ extern int g_fused_kind;
 extern int g_fused_prefetch;
 extern int g_fused_occ;
 extern int g_gemm_big_tiles;
+extern int g_fused_weight_ratio_x100;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -234,6 +235,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
     if (value < 0 || value > 2) return GML_E_BADARG;
     g_fused_kind = (int)value; return GML_OK;
   }
+  if (!strcmp(name, "fused_weight_ratio_x100")) { g_fused_weight_ratio_x100 = (int)value; return GML_OK; }
   if (!strcmp(name, "gemm_big_tiles")) { g_gemm_big_tiles = value ? 1 : 0; return GML_OK; }
   if (!strcmp(name, "fused_occ")) {
     if (value != 4 && value != 5) return GML_E_BADARG;

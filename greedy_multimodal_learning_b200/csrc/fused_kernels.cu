@@ -1089,12 +1089,13 @@ int dispatch_l2_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
 }  // namespace
 
 static bool use_l2_kind() { return g_fused_kind == 2 || g_fused_kind == 0; }
+int g_fused_weight_ratio_x100 = 100;  // tunable: max (FC weight bytes) / (group feature-map bytes), in percent
 static bool weights_ok(const FusedCfg& f) {
   // per-sample FC weights are re-read from L2 for every group: only worth it while they are small
   // next to the group's feature-map bytes (MMTM4's 512x7^2 goes the streaming way)
   const double w_bytes = 16.0 * f.c * f.d;
   const double group_bytes = 2.0 * f.g * 2.0 * f.c * f.hw * 4.0;
-  return w_bytes <= group_bytes;
+  return w_bytes * 100.0 <= group_bytes * g_fused_weight_ratio_x100;
 }
 static bool pick_cfg(int n, int c, int hw, int d, FusedCfg* f, bool* l2, bool bwd) {
   if (use_l2_kind()) {
