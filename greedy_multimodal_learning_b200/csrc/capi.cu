@@ -67,6 +67,28 @@ static void prof_drain() {
   g_prof_pending.clear();
 }
 
+// Lazily created per-thread, per-device helper stream: lets the weight-gradient GEMMs of the streaming
+// backward run beside the dZ GEMM + gradient-apply pass (fork/join with events; capturable in a CUDA graph).
+struct SideStream {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+  static thread_local SideStream ss[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& s = ss[dev];
+  if (s.device != dev) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    s.device = dev;
+  }
+  return &s;
+}
+std::atomic<int> g_overlap_wgrad{1};
+
 namespace {
 
 struct Dims {
@@ -223,6 +245,7 @@ extern int g_fused_prefetch;
 extern int g_fused_occ;
 extern int g_gemm_big_tiles;
 extern int g_fused_weight_ratio_x100;
+extern int g_fused_group_kb;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -236,6 +259,8 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
     g_fused_kind = (int)value; return GML_OK;
   }
   if (!strcmp(name, "fused_weight_ratio_x100")) { g_fused_weight_ratio_x100 = (int)value; return GML_OK; }
+  if (!strcmp(name, "overlap_wgrad")) { g_overlap_wgrad.store(value ? 1 : 0); return GML_OK; }
+  if (!strcmp(name, "fused_group_kb")) { g_fused_group_kb = (int)value; return GML_OK; }
   if (!strcmp(name, "gemm_big_tiles")) { g_gemm_big_tiles = value ? 1 : 0; return GML_OK; }
   if (!strcmp(name, "fused_occ")) {
     if (value != 4 && value != 5) return GML_E_BADARG;
@@ -359,7 +384,7 @@ extern "C" size_t gml_mmtm_bwd_workspace_bytes(const gml_mmtm_dims* dims) {
   if (!dims || dims->n < 0) return 0;
   const size_t n = (size_t)dims->n, ldz = (size_t)dims->c_v + dims->c_s, dd = (size_t)dims->d;
   // de_a [N,c_v] + de_b [N,c_s] + dh [2N,D] + dz [2N,ldz]   (2N rows cover mode 3)
-  return 256 + sizeof(float) * (n * ldz + 2 * n * dd + 2 * n * ldz) + 4 * 256 + gemm_workspace_bytes();
+  return 256 + sizeof(float) * (n * ldz + 2 * n * dd + 2 * n * ldz) + 4 * 256 + 2 * gemm_workspace_bytes();
 }
 
 extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a, const float* b, const float* w_sq,
@@ -391,7 +416,43 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   float* dz = carve((size_t)2 * d.n * d.ldz);
   void* gws = wp;
   const size_t gws_bytes = gemm_workspace_bytes();
+  void* gws2 = wp + round_up(gws_bytes, 256);  // second split-K workspace for the side stream
   GML_TRY(prepare_gemm_workspace(gws, gws_bytes, st));
+  GML_TRY(prepare_gemm_workspace(gws2, gws_bytes, st));
+
+  // weight gradients over the whole batch (reduction over samples inside one CTA per tile or split-K
+  // with an ordered fold: deterministic, no atomics)
+  auto weight_grads = [&](cudaStream_t ws_stream, void* ws_mem) -> int {
+    GemmDesc gw[2];
+    int cw = 0;
+    if (d_w_v) {
+      if (la) gw[cw++] = GemmDesc{de_a, h, d_w_v, nullptr, nullptr, d.c_v, d.d, d.n, d.c_v, d.d, d.d, 0, 0, 0, kActNone, 0};
+      else GML_TRY(launch_fill_zero(d_w_v, (size_t)d.c_v * d.d, ws_stream));
+    }
+    if (d_w_s) {
+      if (lb) gw[cw++] = GemmDesc{de_b, h + (size_t)d.hoff * d.d, d_w_s, nullptr, nullptr, d.c_s, d.d, d.n, d.c_s, d.d, d.d, 0, 0, 0, kActNone, 0};
+      else GML_TRY(launch_fill_zero(d_w_s, (size_t)d.c_s * d.d, ws_stream));
+    }
+    if (cw) GML_TRY(launch_gemm(gw, cw, ws_stream, ws_mem, gws_bytes));
+    if (d_w_sq) {
+      GemmDesc gq{dh, z, d_w_sq, nullptr, nullptr, d.d, d.ldz, d.zrows, d.d, d.ldz, d.ldz, 0, 0, 0, kActNone, 0};
+      GML_TRY(launch_gemm(&gq, 1, ws_stream, ws_mem, gws_bytes));
+    }
+    ColsumSeg segs[3];
+    int nseg = 0;
+    if (d_b_v) {
+      if (la) segs[nseg++] = ColsumSeg{de_a, d_b_v, d.n, d.c_v, d.c_v, nullptr, nullptr, 1.f, 0.f};
+      else GML_TRY(launch_fill_zero(d_b_v, d.c_v, ws_stream));
+    }
+    if (d_b_s) {
+      if (lb) segs[nseg++] = ColsumSeg{de_b, d_b_s, d.n, d.c_s, d.c_s, nullptr, nullptr, 1.f, 0.f};
+      else GML_TRY(launch_fill_zero(d_b_s, d.c_s, ws_stream));
+    }
+    if (d_b_sq) segs[nseg++] = ColsumSeg{dh, d_b_sq, d.zrows, d.d, d.d, nullptr, nullptr, 1.f, 0.f};
+    if (nseg) GML_TRY(launch_colsums(segs, nseg, ws_stream));
+    return GML_OK;
+  };
+  bool wgrad_done = false;
 
   const bool can_fuse = !(flags & GML_F_FORCE_STREAMING) && la && lb &&
                         fused_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
@@ -434,6 +495,16 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
       } else {
         GML_TRY(launch_gemm(&gb, 1, st, gws, gws_bytes));
       }
+      // the weight gradients only need dE / dH: with the whole batch in one chunk they run on the side
+      // stream, next to the dZ GEMM and the (HBM-bound) gradient-apply pass
+      SideStream* side = (cn == d.n && g_overlap_wgrad.load()) ? side_stream() : nullptr;
+      if (side) {
+        GML_CUDA_TRY(cudaEventRecord(side->fork, st));
+        GML_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        GML_TRY(weight_grads(side->stream, gws2));
+        GML_CUDA_TRY(cudaEventRecord(side->join, side->stream));
+        wgrad_done = true;
+      }
       // 3. dZ = dH Wsq
       GemmDesc gz[2];
       gz[0] = GemmDesc{dh_a, w_sq, dz + (size_t)n0 * d.ldz, nullptr, nullptr, cn, d.ldz, d.d, d.d, d.ldz, d.ldz, 0, 1, 0, kActNone, 0};
@@ -451,39 +522,10 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
       ScaleSeg sb{go_b + ob, d_b + ob, lb ? g_b + (size_t)n0 * d.c_s : run_s, dz + (size_t)(d.hoff + n0) * d.ldz,
                   cn * d.c_s, d.hw_s, d.c_s, lb ? 0 : 1, d.ldz, d.c_v, gate_scale};
       GML_TRY(launch_plane_scale(sa, sb, true, st));
+      if (side) GML_CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
     }
   }
 
-  // 5. weight gradients over the whole batch (reduction over samples inside one CTA per tile:
-  //    deterministic, no atomics)
-  GemmDesc gw[2];
-  int cw = 0;
-  if (d_w_v) {
-    if (la) gw[cw++] = GemmDesc{de_a, h, d_w_v, nullptr, nullptr, d.c_v, d.d, d.n, d.c_v, d.d, d.d, 0, 0, 0, kActNone, 0};
-    else GML_TRY(launch_fill_zero(d_w_v, (size_t)d.c_v * d.d, st));
-  }
-  if (d_w_s) {
-    if (lb) gw[cw++] = GemmDesc{de_b, h + (size_t)d.hoff * d.d, d_w_s, nullptr, nullptr, d.c_s, d.d, d.n, d.c_s, d.d, d.d, 0, 0, 0, kActNone, 0};
-    else GML_TRY(launch_fill_zero(d_w_s, (size_t)d.c_s * d.d, st));
-  }
-  if (cw) GML_TRY(launch_gemm(gw, cw, st, gws, gws_bytes));
-  if (d_w_sq) {
-    GemmDesc gq{dh, z, d_w_sq, nullptr, nullptr, d.d, d.ldz, d.zrows, d.d, d.ldz, d.ldz, 0, 0, 0, kActNone, 0};
-    GML_TRY(launch_gemm(&gq, 1, st, gws, gws_bytes));
-  }
-  {
-    ColsumSeg segs[3];
-    int nseg = 0;
-    if (d_b_v) {
-      if (la) segs[nseg++] = ColsumSeg{de_a, d_b_v, d.n, d.c_v, d.c_v, nullptr, nullptr, 1.f, 0.f};
-      else GML_TRY(launch_fill_zero(d_b_v, d.c_v, st));
-    }
-    if (d_b_s) {
-      if (lb) segs[nseg++] = ColsumSeg{de_b, d_b_s, d.n, d.c_s, d.c_s, nullptr, nullptr, 1.f, 0.f};
-      else GML_TRY(launch_fill_zero(d_b_s, d.c_s, st));
-    }
-    if (d_b_sq) segs[nseg++] = ColsumSeg{dh, d_b_sq, d.zrows, d.d, d.d, nullptr, nullptr, 1.f, 0.f};
-    if (nseg) GML_TRY(launch_colsums(segs, nseg, st));
-  }
+  if (!wgrad_done) GML_TRY(weight_grads(st, gws));
   return GML_OK;
 }

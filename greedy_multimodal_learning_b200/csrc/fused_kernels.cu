@@ -40,6 +40,7 @@ int g_fused_cluster = 0;   // tunables (gml_set_tunable): 0 = automatic
 int g_fused_threads = 0;
 int g_fused_kind = 0;      // 0 auto, 1 shared-memory resident, 2 L2 resident
 int g_fused_occ = 4;       // L2-resident kernels: CTAs per SM the register budget is compiled for (4: 64 regs, 5: 48)
+int g_fused_group_kb = 128;  // L2-resident kernels: take 2 samples per cluster while 2 slices <= this many KB per CTA
 int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch on/off (measured: no gain, off)
 long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
@@ -1022,7 +1023,7 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
   f.n = n; f.c = c; f.hw = hw; f.d = d; f.cs = cs; f.threads = 256;
   f.cq = c / cs; f.dq = d / cs;
   const size_t slice = (size_t)2 * f.cq * hw * sizeof(float);
-  f.g = slice * 2 <= 131072 ? 2 : 1;  // two samples per cluster while the CTA's share stays <= 128 KB
+  f.g = slice * 2 <= (size_t)g_fused_group_kb * 1024 ? 2 : 1;  // two samples per cluster while the CTA's share stays small
   if (f.g > n) f.g = n;
   f.pl = f.g * 2 * f.cq;
   if (f.pl > f.threads || f.dq * f.g > f.threads) return false;

@@ -170,6 +170,121 @@ __global__ void __launch_bounds__(kThreads) plane_scale_kernel(ScaleLaunch p) {
   }
 }
 
+
+// ---- planes that are not a multiple of 4 floats (HW = 49): four adjacent planes form one span of
+// HW float4 that IS 16-byte tileable.  A lane group owns such a quad; every element picks its plane
+// with three compares.  Same traffic and coalescing as the vector path above, ~4x the ALU work per
+// element (irrelevant: the kernels are HBM-bound).
+__device__ __forceinline__ int plane_in_quad(int e, int hw) { return (e >= hw) + (e >= 2 * hw) + (e >= 3 * hw); }
+
+template <int L, bool DUAL, int EPI>
+__global__ void __launch_bounds__(kThreads) quad_reduce_kernel(ReduceLaunch p) {
+  const int seg_id = (blockIdx.x >= (unsigned)p.seg_blocks0) ? 1 : 0;
+  const ReduceSeg s = seg_id ? p.seg[1] : p.seg[0];
+  const int block_in_seg = blockIdx.x - (seg_id ? p.seg_blocks0 : 0);
+  const int hw = s.hw;
+  constexpr int kQuadsPerBlock = kThreads / L;
+  const int lane = threadIdx.x % L;
+  const int quad = block_in_seg * kQuadsPerBlock + threadIdx.x / L;
+  const int nquads = s.rows >> 2;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (quad < nquads) {
+    const size_t base = (size_t)quad * 4 * hw;
+    const float4* x4 = reinterpret_cast<const float4*>(s.x + base);
+    const float4* y4 = DUAL ? reinterpret_cast<const float4*>(s.y + base) : nullptr;
+    const uint64_t pol = p.keep_in_l2 ? policy_evict_last() : policy_evict_first();
+    for (int j0 = lane; j0 < hw; j0 += 8 * L) {
+      float4 xv[8], yv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * L;
+        xv[u] = j < hw ? ldg_hint(x4 + j, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (DUAL) yv[u] = j < hw ? ldg_stream(y4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e0 = 4 * (j0 + u * L);
+        float v[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+        if constexpr (DUAL) { v[0] *= yv[u].x; v[1] *= yv[u].y; v[2] *= yv[u].z; v[3] *= yv[u].w; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int pq = plane_in_quad(e0 + q, hw);  // out-of-range lanes carry zeros
+#pragma unroll
+          for (int t = 0; t < 4; ++t) acc[t] += (pq == t) ? v[q] : 0.f;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc[t] = group_sum<L>(acc[t]);
+  if (quad < nquads && lane < 4) {
+    const int row = quad * 4 + lane;
+    const float a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+    const int n = row / s.c, c = row - n * s.c;
+    const size_t o = (size_t)n * s.out_ld + s.out_off + c;
+    if constexpr (EPI == kEpiMean) {
+      s.out[o] = a / (float)hw;
+    } else {
+      const float g = s.gate[row];
+      s.out[o] = a * s.mul * g * (1.f - g);
+    }
+  }
+}
+
+template <int L, bool HAS_ADD>
+__global__ void __launch_bounds__(kThreads) quad_scale_kernel(ScaleLaunch p) {
+  const int seg_id = (blockIdx.x >= (unsigned)p.seg_blocks0) ? 1 : 0;
+  const ScaleSeg s = seg_id ? p.seg[1] : p.seg[0];
+  const int block_in_seg = blockIdx.x - (seg_id ? p.seg_blocks0 : 0);
+  const int hw = s.hw;
+  constexpr int kQuadsPerBlock = kThreads / L;
+  const int lane = threadIdx.x % L;
+  const int quad = block_in_seg * kQuadsPerBlock + threadIdx.x / L;
+  if (quad >= (s.rows >> 2)) return;
+  float sc[4], ad[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int row = quad * 4 + t;
+    const int n = row / s.c, c = row - n * s.c;
+    sc[t] = s.scale[s.scale_bcast ? c : row] * s.mul;
+    ad[t] = 0.f;
+    if constexpr (HAS_ADD) ad[t] = s.add[(size_t)n * s.add_ld + s.add_off + c] / (float)hw;
+  }
+  const size_t base = (size_t)quad * 4 * hw;
+  const float4* x4 = reinterpret_cast<const float4*>(s.x + base);
+  float4* o4 = reinterpret_cast<float4*>(s.out + base);
+  const uint64_t pol = policy_evict_first();
+  for (int j0 = lane; j0 < hw; j0 += 8 * L) {
+    float4 xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * L;
+      if (j < hw) xv[u] = ldg_hint(x4 + j, pol);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * L;
+      if (j < hw) {
+        float v[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int pq = plane_in_quad(4 * j + q, hw);
+          const float m = pq == 0 ? sc[0] : (pq == 1 ? sc[1] : (pq == 2 ? sc[2] : sc[3]));
+          const float a = pq == 0 ? ad[0] : (pq == 1 ? ad[1] : (pq == 2 ? ad[2] : ad[3]));
+          v[q] = fmaf(v[q], m, a);
+        }
+        stg_stream(o4 + j, make_float4(v[0], v[1], v[2], v[3]));
+      }
+    }
+  }
+}
+
+inline int pick_quad_lanes(int hw) {  // hw float4 per quad
+  int l = 4;
+  while (l < 32 && hw > l * 8) l <<= 1;
+  return l;
+}
+
 // lanes per plane: keep ~4-8 128-bit loads per lane
 inline int pick_lanes(int hw, bool vec) {
   const int items = vec ? hw / 4 : hw;
@@ -215,7 +330,29 @@ static int reduce_dispatch(ReduceSeg a, ReduceSeg b, bool keep_in_l2, cudaStream
   auto vec_ok = [](const ReduceSeg& s) {
     return s.hw % 4 == 0 && aligned16(s.x) && (!DUAL || aligned16(s.y));
   };
+  auto quad_ok = [](const ReduceSeg& s) {
+    return s.hw % 4 != 0 && s.rows % 4 == 0 && aligned16(s.x) && (!DUAL || aligned16(s.y));
+  };
   auto launch = [&](const ReduceSeg& s0, const ReduceSeg* s1) -> int {
+    if (quad_ok(s0) && (!s1 || quad_ok(*s1))) {
+      const int lanes = pick_quad_lanes(s0.hw);
+      const int qpb = kThreads / lanes;
+      ReduceLaunch p;
+      p.keep_in_l2 = keep_in_l2 ? 1 : 0;
+      p.seg[0] = s0;
+      p.seg_blocks0 = ceil_div(s0.rows / 4, qpb);
+      int blocks = p.seg_blocks0;
+      if (s1) { p.seg[1] = *s1; blocks += ceil_div(s1->rows / 4, qpb); } else { p.seg[1] = s0; p.seg[1].rows = 0; }
+      LaunchScope ls(DUAL ? kTagDGate : kTagMean, st);
+      switch (lanes) {
+        case 4: quad_reduce_kernel<4, DUAL, EPI><<<blocks, kThreads, 0, st>>>(p); break;
+        case 8: quad_reduce_kernel<8, DUAL, EPI><<<blocks, kThreads, 0, st>>>(p); break;
+        case 16: quad_reduce_kernel<16, DUAL, EPI><<<blocks, kThreads, 0, st>>>(p); break;
+        default: quad_reduce_kernel<32, DUAL, EPI><<<blocks, kThreads, 0, st>>>(p); break;
+      }
+      GML_LAUNCH_CHECK();
+      return GML_OK;
+    }
     const bool vec = vec_ok(s0);
     const int lanes = pick_lanes(s0.hw, vec);
     const int rpb = kThreads / lanes;
@@ -235,7 +372,7 @@ static int reduce_dispatch(ReduceSeg a, ReduceSeg b, bool keep_in_l2, cudaStream
     return launch_reduce_l<0, false, DUAL, EPI>(lanes, p, blocks, st);
   };
   const bool has_a = a.rows > 0, has_b = b.rows > 0;
-  if (has_a && has_b && a.hw == b.hw && vec_ok(a) == vec_ok(b)) return launch(a, &b);
+  if (has_a && has_b && a.hw == b.hw && vec_ok(a) == vec_ok(b) && quad_ok(a) == quad_ok(b)) return launch(a, &b);
   if (has_a) GML_TRY(launch(a, nullptr));
   if (has_b) GML_TRY(launch(b, nullptr));
   return GML_OK;
@@ -251,7 +388,32 @@ int launch_plane_dgate(const ReduceSeg& a, const ReduceSeg& b, bool keep_in_l2, 
 
 int launch_plane_scale(const ScaleSeg& a, const ScaleSeg& b, bool has_add, cudaStream_t st) {
   auto vec_ok = [](const ScaleSeg& s) { return s.hw % 4 == 0 && aligned16(s.x) && aligned16(s.out); };
+  auto quad_ok = [](const ScaleSeg& s) {
+    return s.hw % 4 != 0 && s.rows % 4 == 0 && aligned16(s.x) && aligned16(s.out);
+  };
   auto launch = [&](const ScaleSeg& s0, const ScaleSeg* s1) -> int {
+    if (quad_ok(s0) && (!s1 || quad_ok(*s1))) {
+      const int lanes = pick_quad_lanes(s0.hw);
+      const int qpb = kThreads / lanes;
+      ScaleLaunch p;
+      p.seg[0] = s0;
+      p.seg_blocks0 = ceil_div(s0.rows / 4, qpb);
+      int blocks = p.seg_blocks0;
+      if (s1) { p.seg[1] = *s1; blocks += ceil_div(s1->rows / 4, qpb); } else { p.seg[1] = s0; p.seg[1].rows = 0; }
+      LaunchScope ls(has_add ? kTagScaleBwd : kTagScaleFwd, st);
+#define GML_QS(LL)                                                              \
+  if (has_add) quad_scale_kernel<LL, true><<<blocks, kThreads, 0, st>>>(p);     \
+  else quad_scale_kernel<LL, false><<<blocks, kThreads, 0, st>>>(p)
+      switch (lanes) {
+        case 4: GML_QS(4); break;
+        case 8: GML_QS(8); break;
+        case 16: GML_QS(16); break;
+        default: GML_QS(32); break;
+      }
+#undef GML_QS
+      GML_LAUNCH_CHECK();
+      return GML_OK;
+    }
     const bool vec = vec_ok(s0);
     const int lanes = pick_lanes(s0.hw, vec);
     const int rpb = kThreads / lanes;
@@ -274,7 +436,7 @@ int launch_plane_scale(const ScaleSeg& a, const ScaleSeg& b, bool has_add, cudaS
                    : launch_scale_l<0, false, false>(lanes, p, blocks, st);
   };
   const bool has_a = a.rows > 0, has_b = b.rows > 0;
-  if (has_a && has_b && a.hw == b.hw && vec_ok(a) == vec_ok(b)) return launch(a, &b);
+  if (has_a && has_b && a.hw == b.hw && vec_ok(a) == vec_ok(b) && quad_ok(a) == quad_ok(b)) return launch(a, &b);
   if (has_a) GML_TRY(launch(a, nullptr));
   if (has_b) GML_TRY(launch(b, nullptr));
   return GML_OK;

@@ -33,6 +33,9 @@ VARIANTS = {
     "l2_cs4_occ5": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 4, "fused_occ": 5}),
     "l2_cs4_anyw": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 4, "fused_weight_ratio_x100": 100000}),
     "l2_cs8_anyw": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 8, "fused_weight_ratio_x100": 100000}),
+    "l2_cs8_g2": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 8, "fused_group_kb": 256}),
+    "l2_cs4_g1": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 4, "fused_group_kb": 64}),
+    "l2_cs8_g1": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 8, "fused_group_kb": 64, "fused_weight_ratio_x100": 100000}),
     "l2_cs8_nopf": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 8, "fused_prefetch": 0}),
     "l2_cs4_nopf": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 4, "fused_prefetch": 0}),
     "l2_cs4": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 4}),
@@ -73,7 +76,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 rc = fwd(flags)
                 if rc == -5:
