@@ -246,6 +246,7 @@ extern int g_fused_occ;
 extern int g_gemm_big_tiles;
 extern int g_fused_weight_ratio_x100;
 extern int g_fused_group_kb;
+extern int g_fused_stash_kb;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -260,13 +261,14 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   }
   if (!strcmp(name, "fused_weight_ratio_x100")) { g_fused_weight_ratio_x100 = (int)value; return GML_OK; }
   if (!strcmp(name, "overlap_wgrad")) { g_overlap_wgrad.store(value ? 1 : 0); return GML_OK; }
+  if (!strcmp(name, "fused_stash_kb")) { g_fused_stash_kb = value < 0 ? 0 : (value > 200 ? 200 : (int)value); return GML_OK; }
   if (!strcmp(name, "fused_group_kb")) { g_fused_group_kb = (int)value; return GML_OK; }
   if (!strcmp(name, "gemm_big_tiles")) { g_gemm_big_tiles = value ? 1 : 0; return GML_OK; }
   if (!strcmp(name, "fused_occ")) {
     if (value != 4 && value != 5) return GML_E_BADARG;
     g_fused_occ = (int)value; return GML_OK;
   }
-  if (!strcmp(name, "fused_prefetch")) { g_fused_prefetch = value ? 1 : 0; return GML_OK; }
+  if (!strcmp(name, "fused_prefetch")) { g_fused_prefetch = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "fused_trace_ptr")) { g_fused_trace = reinterpret_cast<long long*>(value); return GML_OK; }
   if (!strcmp(name, "fused_threads")) {
     if (value != 0 && value != 256 && value != 512) return GML_E_BADARG;

@@ -41,7 +41,8 @@ int g_fused_threads = 0;
 int g_fused_kind = 0;      // 0 auto, 1 shared-memory resident, 2 L2 resident
 int g_fused_occ = 4;       // L2-resident kernels: CTAs per SM the register budget is compiled for (4: 64 regs, 5: 48)
 int g_fused_group_kb = 128;  // L2-resident kernels: take 2 samples per cluster while 2 slices <= this many KB per CTA
-int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch on/off (measured: no gain, off)
+int g_fused_stash_kb = 24; // L2-resident kernels: shared memory per CTA used to stash planes between the passes (24 KB measured best; 46+ costs occupancy)
+int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch look-ahead distance in groups (0 = off)
 long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
 namespace {
@@ -64,6 +65,7 @@ struct FusedCfg {
   long long* trace;  // nullptr unless phase tracing is on: [cta < 8][iter < 16][16 stamps]
   int prefetch;      // L2-resident kernels: issue bulk L2 prefetches of the CTA's planes up front
   int trace_first;   // first CTA of the traced window (L2-resident kernels)
+  int keep_planes;   // L2-resident kernels: the first keep_planes planes of a CTA are stashed in shared memory
 };
 
 #define GML_STAMP(k)                                                                       \
@@ -619,6 +621,7 @@ bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out
   f.trace = g_fused_trace;
   f.trace_first = 0;
   f.prefetch = 0;
+  f.keep_planes = 0;
   const size_t total = f.data_bytes + extras_bytes(f, true);
   if (total > (cs == 4 ? 232448u : 115000u)) return false;
   *out = f;
@@ -717,10 +720,13 @@ int dispatch_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
 struct L2Smem {
   float* vec_a; float* vec_b; float* psum; float* scale; float* addv; float* bias_h; float* bias_g; float* part;
 };
-__host__ __device__ inline size_t l2_smem_bytes(const FusedCfg& f, bool bwd) {
+__host__ __device__ inline size_t l2_small_bytes(const FusedCfg& f, bool bwd) {
   size_t b = (size_t)f.g * 2 * f.c * 4 + (size_t)f.g * f.d * 4 + 3 * (size_t)f.pl * 4 + ((size_t)f.dq + 2 * f.cq) * 4;
   if (bwd) b += (size_t)f.threads * f.g * 4;
-  return b + 16;
+  return (b + 16 + 127) / 128 * 128;
+}
+__host__ __device__ inline size_t l2_smem_bytes(const FusedCfg& f, bool bwd) {
+  return l2_small_bytes(f, bwd) + (size_t)f.keep_planes * f.hw * 4;
 }
 __device__ __forceinline__ L2Smem l2_carve(unsigned char* p, const FusedCfg& f) {
   L2Smem s;
@@ -742,6 +748,9 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   const int rank = (int)cluster.block_rank();
   const int grp = blockIdx.x / f.cs;
   const L2Smem s = l2_carve(smem_raw, f);
+  // per-thread stash: a thread parks the values it loaded in pass 1 and picks the SAME elements up in
+  // pass 2 -- shared memory used as extra register space, no synchronisation, no L2 re-read
+  float4* stash = reinterpret_cast<float4*>(smem_raw + l2_small_bytes(f, false));
   const int tid = threadIdx.x;
   const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
   for (int i = tid; i < f.dq; i += T) s.bias_h[i] = __ldg(a.b_sq + rank * f.dq + i);
@@ -760,12 +769,15 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
 #define GML_STAMP2(k) do { if (stamp_me) f.trace[((size_t)(blockIdx.x - f.trace_first) * 16 + iter) * 16 + (k)] = clock64(); } while (0)
   GML_STAMP2(0);
 
-  // ---- whole slice on its way HBM -> L2 before the first register load is issued ---------------
-  if (f.prefetch) {
-    for (int p = tid; p < vplanes; p += T) {
+  // ---- look-ahead: while this cluster is busy, the planes of the cluster that will run `prefetch`
+  // groups later are pulled HBM -> L2 by the bulk-prefetch engine (no registers, no shared memory)
+  if (f.prefetch > 0 && grp + f.prefetch < f.n_groups) {
+    const int pn0 = (grp + f.prefetch) * f.g;
+    const int pvplanes = min(f.g, f.n - pn0) * 2 * f.cq;
+    for (int p = tid; p < pvplanes; p += T) {
       int g, mod, cl;
       plane_coords(f, p, g, mod, cl);
-      bulk_prefetch_l2((mod ? a.b : a.a) + ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw,
+      bulk_prefetch_l2((mod ? a.b : a.a) + ((size_t)(pn0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw,
                        (uint32_t)f.hw * 4u, pol_keep);
     }
   }
@@ -776,15 +788,21 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
     const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) +
                                                        ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const bool kept = p < f.keep_planes;
+    const uint64_t pol = kept ? pol_drop : pol_keep;  // stashed planes need no L2 residency
     for (int i0 = 0; i0 < hw4; i0 += 8 * L) {
       float4 x[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + lane + u * L;
-        x[u] = i < hw4 ? ldg_hint(xv + i, pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[u] = i < hw4 ? ldg_hint(xv + i, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { a0 += x[u].x; a1 += x[u].y; a2 += x[u].z; a3 += x[u].w; }
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + lane + u * L;
+        if (kept && i < hw4) stash[(size_t)p * hw4 + i] = x[u];
+        a0 += x[u].x; a1 += x[u].y; a2 += x[u].z; a3 += x[u].w;
+      }
     }
     const float t = group_sum<L>((a0 + a1) + (a2 + a3));
     if (lane == 0) s.psum[p] = t;
@@ -842,12 +860,13 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
     const size_t off = ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
     const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) + off);
     float4* o = reinterpret_cast<float4*>((mod ? a.b_out : a.a_out) + off);
+    const bool kept = p < f.keep_planes;
     for (int i0 = 0; i0 < hw4; i0 += 8 * L) {
       float4 x[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + lane + u * L;
-        if (i < hw4) x[u] = ldg_hint(xv + i, pol_drop);
+        if (i < hw4) x[u] = kept ? stash[(size_t)p * hw4 + i] : ldg_hint(xv + i, pol_drop);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -872,6 +891,7 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   const int rank = (int)cluster.block_rank();
   const int grp = blockIdx.x / f.cs;
   const L2Smem s = l2_carve(smem_raw, f);
+  float4* stash = reinterpret_cast<float4*>(smem_raw + l2_small_bytes(f, true));  // see l2_fwd_kernel
   const int tid = threadIdx.x;
   const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
   constexpr int kPlanesPerPass = T / L;
@@ -892,11 +912,13 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const int g = tid / ncol_h, col = tid - g * ncol_h;
     h_pf = __ldg(a.h + (size_t)(n0 + g) * f.d + rank * f.dq + col);
   }
-  if (f.prefetch) {
-    for (int p = tid; p < vplanes; p += T) {
+  if (f.prefetch > 0 && grp + f.prefetch < f.n_groups) {
+    const int pn0 = (grp + f.prefetch) * f.g;
+    const int pvplanes = min(f.g, f.n - pn0) * 2 * f.cq;
+    for (int p = tid; p < pvplanes; p += T) {
       int g, mod, cl;
       plane_coords(f, p, g, mod, cl);
-      const size_t off = ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
+      const size_t off = ((size_t)(pn0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
       bulk_prefetch_l2((mod ? a.go_b : a.go_a) + off, (uint32_t)f.hw * 4u, pol_keep);
       bulk_prefetch_l2((mod ? a.b : a.a) + off, (uint32_t)f.hw * 4u, pol_drop);
     }
@@ -909,13 +931,15 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const float4* gv = reinterpret_cast<const float4*>((mod ? a.go_b : a.go_a) + off);
     const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) + off);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const bool kept = p < f.keep_planes;
+    const uint64_t polg = kept ? pol_drop : pol_keep;
     for (int i0 = 0; i0 < hw4; i0 += 4 * L) {
       float4 x[4], gg[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + lane + u * L;
         if (i < hw4) {
-          gg[u] = ldg_hint(gv + i, pol_keep);
+          gg[u] = ldg_hint(gv + i, polg);
           x[u] = ldg_hint(xv + i, pol_drop);
         } else {
           gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -924,6 +948,8 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + u * L;
+        if (kept && i < hw4) stash[(size_t)p * hw4 + i] = gg[u];
         a0 = fmaf(gg[u].x, x[u].x, a0); a1 = fmaf(gg[u].y, x[u].y, a1);
         a2 = fmaf(gg[u].z, x[u].z, a2); a3 = fmaf(gg[u].w, x[u].w, a3);
       }
@@ -996,12 +1022,13 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const size_t off = ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
     const float4* gv = reinterpret_cast<const float4*>((mod ? a.go_b : a.go_a) + off);
     float4* o = reinterpret_cast<float4*>((mod ? a.d_b : a.d_a) + off);
+    const bool kept = p < f.keep_planes;
     for (int i0 = 0; i0 < hw4; i0 += 8 * L) {
       float4 x[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + lane + u * L;
-        if (i < hw4) x[u] = ldg_hint(gv + i, pol_drop);
+        if (i < hw4) x[u] = kept ? stash[(size_t)p * hw4 + i] : ldg_hint(gv + i, pol_drop);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -1033,7 +1060,9 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
   f.data_bytes = 0;
   f.trace = g_fused_trace;
   f.trace_first = (f.n_groups / 2) * cs;
-  f.prefetch = g_fused_prefetch && ((size_t)hw * 4) % 16 == 0;
+  f.prefetch = ((size_t)hw * 4) % 16 == 0 ? g_fused_prefetch : 0;  // look-ahead distance in groups
+  f.keep_planes = (int)(((size_t)g_fused_stash_kb * 1024) / ((size_t)hw * 4));
+  if (f.keep_planes > f.pl) f.keep_planes = f.pl;
   if ((long long)f.n_groups * cs > 0x7fffffffLL) return false;
   *out = f;
   return true;
@@ -1042,6 +1071,7 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
 template <typename Args, typename K>
 int do_launch_l2(K kern, const Args& args, const FusedCfg& f, bool bwd, cudaStream_t st, int tag) {
   const size_t smem = l2_smem_bytes(f, bwd);
+  if (smem > 48 * 1024) GML_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(f.threads);
   cfg.dynamicSmemBytes = smem;

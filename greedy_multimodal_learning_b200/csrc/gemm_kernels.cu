@@ -239,6 +239,165 @@ __global__ void __launch_bounds__(THREADS, TM == 4 ? 3 : 1) gemm_pipe_kernel(con
   if (tid == 0) *ticket = 0u;  // self-resetting: the workspace can be reused by the next launch
 }
 
+
+// -----------------------------------------------------------------------------------------------
+// Large problems (batch >= ~512): 128x128 tile, 8x8 outputs per thread, BK = 8.  Global loads are
+// staged through registers (next tile prefetched while the current one is multiplied) and written to
+// shared memory TRANSPOSED to [k][row], so that every fragment read is one 128-bit load per 4 rows and
+// one k: 4 LDS.128 per 64 FMA, ~110 registers, two CTAs per SM.  Same split-K / ticket epilogue.
+// -----------------------------------------------------------------------------------------------
+constexpr int GB = 128, GK = 8, GPITCH = GB + 4;
+
+template <bool KC>
+__device__ __forceinline__ float4 big_load(const float* __restrict__ src, int ld, int t0, int tmax, int k0, int kmax,
+                                           int tid) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (KC) {  // src[t * ld + k]: thread -> (row tid/2, k-quad tid%2)
+    const int t = t0 + (tid >> 1), k = k0 + (tid & 1) * 4;
+    if (t < tmax && k < kmax) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)t * ld + k));  // K % 4 == 0
+  } else {   // src[k * ld + t]: thread -> (k tid/32, row-quad tid%32)
+    const int k = k0 + (tid >> 5), t = t0 + (tid & 31) * 4;
+    if (k < kmax && t < tmax) {
+      const float* g = src + (size_t)k * ld + t;
+      if (t + 3 < tmax) v = __ldg(reinterpret_cast<const float4*>(g));
+      else { v.x = g[0]; if (t + 1 < tmax) v.y = g[1]; if (t + 2 < tmax) v.z = g[2]; }
+    }
+  }
+  return v;
+}
+template <bool KC>
+__device__ __forceinline__ void big_store(float (*s)[GPITCH], const float4& v, int tid) {
+  if (KC) {
+    const int row = tid >> 1, kq = (tid & 1) * 4;
+    s[kq + 0][row] = v.x; s[kq + 1][row] = v.y; s[kq + 2][row] = v.z; s[kq + 3][row] = v.w;
+  } else {
+    *reinterpret_cast<float4*>(&s[tid >> 5][(tid & 31) * 4]) = v;
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(THREADS, 2) gemm_big_kernel(const PipeBatch pb) {
+  __shared__ __align__(16) float As[2][GK][GPITCH];
+  __shared__ __align__(16) float Bs[2][GK][GPITCH];
+  __shared__ unsigned int s_ticket;
+  const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
+  const GemmDesc d = prob ? pb.d[1] : pb.d[0];
+  const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+  if (m0 >= d.m || n0 >= d.n) return;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k_begin = split * pb.k_per_split;
+  const int k_end = min(d.k, k_begin + pb.k_per_split);
+  const int nk = k_end > k_begin ? (k_end - k_begin + GK - 1) / GK : 0;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 pa = big_load<A_KC>(d.a, d.lda, m0, d.m, k_begin, k_end, tid);
+  float4 pbv = big_load<B_KC>(d.b, d.ldb, n0, d.n, k_begin, k_end, tid);
+  if (nk > 0) {
+    big_store<A_KC>(As[0], pa, tid);
+    big_store<B_KC>(Bs[0], pbv, tid);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) {
+      pa = big_load<A_KC>(d.a, d.lda, m0, d.m, k_begin + (kt + 1) * GK, k_end, tid);
+      pbv = big_load<B_KC>(d.b, d.ldb, n0, d.n, k_begin + (kt + 1) * GK, k_end, tid);
+    }
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      big_store<A_KC>(As[buf ^ 1], pa, tid);
+      big_store<B_KC>(Bs[buf ^ 1], pbv, tid);
+    }
+    __syncthreads();
+  }
+
+  auto row_of = [&](int i) { return m0 + (i >> 2) * 64 + ty * 4 + (i & 3); };
+  auto col_of = [&](int j) { return n0 + (j >> 2) * 64 + tx * 4 + (j & 3); };
+  if (pb.splits == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = row_of(i);
+      if (m >= d.m) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = col_of(j);
+        if (n >= d.n) continue;
+        float* cp = d.c + (size_t)m * d.ldc + n;
+        *cp = epilogue(d, acc[i][j], m, n, cp);
+      }
+    }
+    return;
+  }
+  float* part = pb.part[prob];
+  const size_t plane = (size_t)d.m * d.n;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = row_of(i);
+    if (m >= d.m) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = col_of(j);
+      if (n < d.n) __stcg(part + (size_t)split * plane + (size_t)m * d.n + n, acc[i][j]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  unsigned int* ticket = pb.tickets + (size_t)prob * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x;
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)pb.splits - 1) return;
+  __threadfence();
+  // fold in split order; acc[][] is reused as the running sum, 8 loads in flight per row
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int sp = 0; sp < pb.splits; ++sp) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = row_of(i);
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = col_of(j);
+        v[j] = (m < d.m && n < d.n) ? __ldcg(part + (size_t)sp * plane + (size_t)m * d.n + n) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = row_of(i);
+    if (m >= d.m) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = col_of(j);
+      if (n >= d.n) continue;
+      float* cp = d.c + (size_t)m * d.ldc + n;
+      *cp = epilogue(d, acc[i][j], m, n, cp);
+    }
+  }
+  if (tid == 0) *ticket = 0u;
+}
+
 bool pipe_ok(const GemmDesc& d) {
   // cp.async moves 16-byte chunks: bases 16-byte aligned, leading dimensions and (for k-contiguous
   // operands) K multiples of 4
@@ -278,8 +437,8 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   }
   if (count == 1) pb.d[1] = descs[0];
   if (count == 2 && descs[0].k != descs[1].k) return GML_E_UNSUPPORTED;
-  // 128x128 tiles (8x8 outputs per thread, 1 CTA per SM at ~250 registers) measured SLOWER than 64x64 at
-  // 2 CTAs per SM on every FC shape of the three blocks (profiles/), so they are opt-in only.
+  // 128x128 tiles (gemm_big_kernel, 8x8 outputs per thread) measured SLOWER than the 64x64 cp.async kernel at
+  // 3 CTAs per SM on every FC shape of the three blocks (profiles/r1_experiments.md), so they are opt-in only.
   const bool big = g_gemm_big_tiles && (long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * count >= 24 && min_k >= 64;
   const int BM = big ? 128 : 64, BN = BM;
   const int tiles_m = ceil_div(max_m, BM), tiles_n = ceil_div(max_n, BN);
@@ -318,14 +477,9 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
 #define GML_GEMM(AK, BKC)                                                                                   \
   do {                                                                                                      \
     if (big) {                                                                                              \
-      const size_t sm = 2 * STAGES * TileGeom<128>::kFloats * sizeof(float);                                 \
-      GML_CUDA_TRY(cudaFuncSetAttribute(gemm_pipe_kernel<AK, BKC, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)sm));                                                           \
-      gemm_pipe_kernel<AK, BKC, 8><<<grid, THREADS, sm, st>>>(pb);                                           \
+      gemm_big_kernel<AK, BKC><<<grid, THREADS, 0, st>>>(pb);                                                \
     } else {                                                                                                \
       const size_t sm = 2 * STAGES * TileGeom<64>::kFloats * sizeof(float);                                  \
-      GML_CUDA_TRY(cudaFuncSetAttribute(gemm_pipe_kernel<AK, BKC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)sm));                                                           \
       gemm_pipe_kernel<AK, BKC, 4><<<grid, THREADS, sm, st>>>(pb);                                           \
     }                                                                                                       \
   } while (0)

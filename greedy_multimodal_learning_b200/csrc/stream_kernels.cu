@@ -206,11 +206,18 @@ __global__ void __launch_bounds__(kThreads) quad_reduce_kernel(ReduceLaunch p) {
         const int e0 = 4 * (j0 + u * L);
         float v[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
         if constexpr (DUAL) { v[0] *= yv[u].x; v[1] *= yv[u].y; v[2] *= yv[u].z; v[3] *= yv[u].w; }
+        const int p0 = plane_in_quad(e0, hw), p3 = plane_in_quad(e0 + 3, hw);  // out-of-range lanes carry zeros
+        if (p0 == p3) {  // the common case: the whole float4 lies inside one plane
+          const float sum4 = (v[0] + v[1]) + (v[2] + v[3]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int pq = plane_in_quad(e0 + q, hw);  // out-of-range lanes carry zeros
+          for (int t = 0; t < 4; ++t) acc[t] += (p0 == t) ? sum4 : 0.f;
+        } else {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) acc[t] += (pq == t) ? v[q] : 0.f;
+          for (int q = 0; q < 4; ++q) {
+            const int pq = plane_in_quad(e0 + q, hw);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[t] += (pq == t) ? v[q] : 0.f;
+          }
         }
       }
     }
@@ -266,12 +273,20 @@ __global__ void __launch_bounds__(kThreads) quad_scale_kernel(ScaleLaunch p) {
       const int j = j0 + u * L;
       if (j < hw) {
         float v[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+        const int p0 = plane_in_quad(4 * j, hw), p3 = plane_in_quad(4 * j + 3, hw);
+        if (p0 == p3) {
+          const float m = p0 == 0 ? sc[0] : (p0 == 1 ? sc[1] : (p0 == 2 ? sc[2] : sc[3]));
+          const float a = p0 == 0 ? ad[0] : (p0 == 1 ? ad[1] : (p0 == 2 ? ad[2] : ad[3]));
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int pq = plane_in_quad(4 * j + q, hw);
-          const float m = pq == 0 ? sc[0] : (pq == 1 ? sc[1] : (pq == 2 ? sc[2] : sc[3]));
-          const float a = pq == 0 ? ad[0] : (pq == 1 ? ad[1] : (pq == 2 ? ad[2] : ad[3]));
-          v[q] = fmaf(v[q], m, a);
+          for (int q = 0; q < 4; ++q) v[q] = fmaf(v[q], m, a);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int pq = plane_in_quad(4 * j + q, hw);
+            const float m = pq == 0 ? sc[0] : (pq == 1 ? sc[1] : (pq == 2 ? sc[2] : sc[3]));
+            const float a = pq == 0 ? ad[0] : (pq == 1 ? ad[1] : (pq == 2 ? ad[2] : ad[3]));
+            v[q] = fmaf(v[q], m, a);
+          }
         }
         stg_stream(o4 + j, make_float4(v[0], v[1], v[2], v[3]));
       }

@@ -21,6 +21,7 @@ from greedy_multimodal_learning_b200 import _lib as L  # noqa: E402
 VARIANTS = {
     # name: (flags, tunables)
     "auto": (0, {}),
+    "auto_biggemm": (0, {"gemm_big_tiles": 1}),
     "stream_c40": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 40}),
     "stream_c64": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 64}),
     "stream_c100": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 100}),
@@ -36,6 +37,14 @@ VARIANTS = {
     "l2_cs8_g2": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 8, "fused_group_kb": 256}),
     "l2_cs4_g1": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 4, "fused_group_kb": 64}),
     "l2_cs8_g1": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 8, "fused_group_kb": 64, "fused_weight_ratio_x100": 100000}),
+    "l2_pf37": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_prefetch": 37}),
+    "l2_pf74": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_prefetch": 74}),
+    "l2_pf148": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_prefetch": 148}),
+    "l2_auto": (L.F_FORCE_FUSED, {"fused_kind": 2}),
+    "l2_stash0": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_stash_kb": 0}),
+    "l2_stash24": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_stash_kb": 24}),
+    "l2_stash46": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_stash_kb": 46}),
+    "l2_stash100": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_stash_kb": 100}),
     "l2_cs8_nopf": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 8, "fused_prefetch": 0}),
     "l2_cs4_nopf": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 4, "fused_prefetch": 0}),
     "l2_cs4": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 4}),
@@ -76,7 +85,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 rc = fwd(flags)
                 if rc == -5:
