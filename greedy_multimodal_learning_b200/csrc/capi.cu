@@ -252,7 +252,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
   if (!strcmp(name, "l2_chunk_mb")) { g_l2_chunk_mb.store(value < 1 ? 1 : (long)value); return GML_OK; }
   if (!strcmp(name, "fused_cluster")) {
-    if (value != 0 && value != 4 && value != 8) return GML_E_BADARG;
+    if (value != 0 && value != 4 && value != 8 && value != 16) return GML_E_BADARG;
     g_fused_cluster = (int)value; return GML_OK;
   }
   if (!strcmp(name, "fused_kind")) {

@@ -1072,6 +1072,7 @@ template <typename Args, typename K>
 int do_launch_l2(K kern, const Args& args, const FusedCfg& f, bool bwd, cudaStream_t st, int tag) {
   const size_t smem = l2_smem_bytes(f, bwd);
   if (smem > 48 * 1024) GML_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (f.cs > 8) GML_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(f.threads);
   cfg.dynamicSmemBytes = smem;

@@ -41,6 +41,8 @@ VARIANTS = {
     "l2_pf74": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_prefetch": 74}),
     "l2_pf148": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_prefetch": 148}),
     "l2_auto": (L.F_FORCE_FUSED, {"fused_kind": 2}),
+    "l2_cs16": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 16}),
+    "l2_cs16_g2": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_cluster": 16, "fused_group_kb": 256}),
     "l2_stash0": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_stash_kb": 0}),
     "l2_stash24": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_stash_kb": 24}),
     "l2_stash46": (L.F_FORCE_FUSED, {"fused_kind": 2, "fused_stash_kb": 46}),
