@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import gin_lite
 
 
 class Callback(object):
@@ -236,3 +237,129 @@ class Bias_Mitigation_Random(Callback):
     def on_epoch_begin(self, epoch, logs):
         if epoch >= self.starting_epoch:
             self.unlock = True
+
+
+# ---------------------------------------------------------------------------------------------
+# Auxiliary callbacks named by the reference's gin files (`train.callbacks=[...]`,
+# configs/training*.gin) and by its default callback set (src/training_loop.py:27-51).  Host
+# logic only; kept so that the five config files run unchanged.
+# ---------------------------------------------------------------------------------------------
+class CompletedStopping(Callback):
+    """Stop after `patience` epochs whose `monitor` equals 100 (reference src/callbacks.py:306-333;
+    the counter never resets between non-perfect epochs)."""
+
+    def __init__(self, *, monitor='acc', patience=5, verbose=True):
+        super().__init__()
+        self.monitor, self.patience, self.verbose = monitor, patience, verbose
+        self.stopped_epoch = 0
+
+    def on_train_begin(self, logs):
+        self.stopped_epoch, self.counter = 0, 0
+
+    def on_epoch_end(self, epoch, logs):
+        self.counter += int(logs[self.monitor] == 100)
+        if self.counter >= self.patience:
+            self.stopped_epoch = epoch
+            self.model_pytoune.stop_training = True
+
+    def on_train_end(self, logs):
+        if self.stopped_epoch > 0 and self.verbose:
+            print('Epoch %05d: completed stopping' % (self.stopped_epoch + 1))
+
+
+class ReduceLROnPlateau_PyTorch(Callback):
+    """torch ReduceLROnPlateau on an epoch log key (reference src/callbacks.py:336-351; the
+    `verbose=` argument it passes no longer exists in torch 2.11 and is dropped)."""
+
+    def __init__(self, metric, factor=0.3, patience=10):
+        self.metric, self.factor, self.patience = metric, factor, patience
+
+    def on_train_begin(self, logs):
+        self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(
+            self.optimizer, mode='min', factor=self.factor, patience=self.patience, threshold=0.001,
+            threshold_mode='rel', cooldown=0, min_lr=1e-6, eps=1e-08)
+
+    def on_epoch_end(self, epoch, logs):
+        self.scheduler.step(logs[self.metric])
+
+
+class LambdaCallback(Callback):
+    """Callback from plain functions (reference src/callbacks.py:354-386)."""
+
+    _HOOKS = ('on_epoch_begin', 'on_epoch_end', 'on_batch_begin', 'on_batch_end', 'on_train_begin', 'on_train_end')
+
+    def __init__(self, **hooks):
+        super().__init__()
+        for name, fn in hooks.items():
+            if name not in self._HOOKS:
+                raise TypeError("LambdaCallback: unknown hook %r" % name)
+            if fn is not None:
+                setattr(self, name, fn)
+
+
+def save_weights(model, optimizer, filename):
+    """`{'model': state_dict, 'optimizer': state_dict}` -- the checkpoint layout the reference
+    writes and reloads (src/utils.py:103-111, src/training_loop.py:78-83)."""
+    torch.save({'model': model.state_dict(), 'optimizer': optimizer.state_dict()}, filename)
+
+
+class ModelCheckpoint(Callback):
+    """Save on improvement of `monitor` (reference src/callbacks.py:389-451)."""
+
+    def __init__(self, filepath, monitor='val_loss', verbose=0, save_best_only=False, mode='auto', period=1):
+        super().__init__()
+        self.filepath, self.monitor, self.verbose = filepath, monitor, verbose
+        self.save_best_only, self.period = save_best_only, period
+        self.epochs_since_last_save = 0
+        if mode not in ('min', 'max'):
+            mode = 'max' if ('acc' in monitor or monitor.startswith('fmeasure')) else 'min'
+        self.monitor_op = np.greater if mode == 'max' else np.less
+        self.best = -np.inf if mode == 'max' else np.inf
+
+    def on_epoch_end(self, epoch, logs=None):
+        logs = logs or {}
+        self.epochs_since_last_save += 1
+        if self.epochs_since_last_save < self.period:
+            return
+        self.epochs_since_last_save = 0
+        if not self.save_best_only:
+            # the reference only saves here when verbose > 0 (src/callbacks.py:448-451); kept
+            if self.verbose > 0:
+                print('Epoch %05d: saving model to %s' % (epoch, self.filepath))
+                save_weights(self.model, self.optimizer, self.filepath)
+            return
+        current = logs.get(self.monitor)
+        if current is None:
+            return
+        if self.monitor_op(current, self.best):
+            if self.verbose > 0:
+                print('Epoch %05d: %s improved from %0.5f to %0.5f, saving model to %s'
+                      % (epoch, self.monitor, self.best, current, self.filepath))
+            self.best = current
+            save_weights(self.model, self.optimizer, self.filepath)
+        elif self.verbose > 0:
+            print('Epoch %05d: %s did not improve' % (epoch, self.monitor))
+
+
+class ProgressionCallback(Callback):
+    """One status line per epoch (the reference redraws a line per batch, src/callbacks.py:454-517)."""
+
+    def __init__(self, other_metrics=('average_iol_current_epoch', 'average_iol')):
+        self.other_metrics = list(other_metrics)
+
+    def on_train_begin(self, logs):
+        self.metrics = ['loss'] + list(self.model_pytoune.metrics_names)
+        self.epochs = self.params['epochs']
+
+    def on_epoch_end(self, epoch, logs):
+        keys = self.metrics + ['val_' + k for k in self.metrics] + self.other_metrics
+        shown = ', '.join('%s: %f' % (k, logs[k]) for k in keys
+                          if isinstance(logs.get(k), (int, float, np.floating, np.integer)))
+        print("Epoch %d/%d %.2fs: %s" % (epoch, self.epochs, logs.get('time', 0.0), shown))
+
+
+# gin names of the reference (`@gin.configurable` in src/callbacks.py)
+for _cls in (Bias_Mitigation_Strong, Bias_Mitigation_Random, CompletedStopping, ReduceLROnPlateau_PyTorch,
+             ProgressionCallback):
+    gin_lite.configurable(_cls)
+del _cls

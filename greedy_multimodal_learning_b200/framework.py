@@ -116,6 +116,21 @@ class StepIterator:
             return []
         return np.concatenate(self.indices_list, axis=0)
 
+    def all_reduce(self, device=None):
+        """Data parallel: make the epoch sums those of the GLOBAL batches so that every rank logs (and
+        schedules the learning rate on) the same numbers.  One small collective per epoch and phase."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        flat = np.concatenate([[self.losses_sum, self.sizes_sum], self.metrics_sum, self.metrics_permodal_sum.ravel()])
+        t = torch.from_numpy(flat).to(device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t)
+        flat = t.cpu().numpy()
+        k = len(self.metrics_sum)
+        self.losses_sum, self.sizes_sum = float(flat[0]), float(flat[1])
+        self.metrics_sum = flat[2:2 + k].copy()
+        self.metrics_permodal_sum = flat[2 + k:].reshape(self.metrics_permodal_sum.shape).copy()
+
     def __iter__(self):
         if self.steps_per_epoch is not None:
             it = zip(range(1, self.steps_per_epoch + 1), _cycle(self.generator))
@@ -311,6 +326,8 @@ class Model_:
                 step['size'] = self._batch_size(x, y)
                 loss, pred_eval, pred_y, yd, record = self._forward_loss(x, y)
                 self._finish_step(step, loss, pred_eval, pred_y, yd, record)
+        if self.data_parallel is not None:
+            it.all_reduce(self.device)
         info = {'%s_loss' % phase: it.loss, '%s_indices' % phase: it.indices,
                 **{'%s_%s' % (phase, k): v for k, v in it.extra_lists.items()},
                 **{'%s_%s' % (phase, k): v for k, v in it.metrics.items()}}
@@ -359,6 +376,8 @@ class Model_:
             with torch.enable_grad():
                 for step, (x, y) in it:
                     self.train_step(step, x, y, cbs)
+            if self.data_parallel is not None:
+                it.all_reduce(self.device)
             logs = {'loss': it.loss, 'train_indices': it.indices,
                     **{'train_%s' % k: v for k, v in it.extra_lists.items()}, **it.metrics}
             val = self._eval_generator(valid_generator, 'val', steps=validation_steps) if valid_generator is not None else {}

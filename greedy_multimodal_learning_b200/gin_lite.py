@@ -94,11 +94,9 @@ def parse_config_files_and_bindings(config_files: Iterable[str], bindings=""):
         if path:
             with open(path) as f:
                 parse_config(f.read())
-    if isinstance(bindings, str):
-        bindings = [b for b in bindings.replace(";", "\n").splitlines()]
-    for b in bindings or []:
-        if b.strip():
-            parse_config(b)
+    if not isinstance(bindings, str):
+        bindings = "\n".join(bindings or [])
+    parse_config(bindings.replace(";", "\n"))
 
 
 def configurable(obj=None):

@@ -12,11 +12,13 @@ import torch
 import torch.nn as nn
 import torchvision.models as models
 
+from . import gin_lite
 from .balanced_mmtm import MMTM_mitigate, get_rescale_weights
 
 MMTM_DIMS = ((128, 128, 4), (256, 256, 4), (512, 512, 4))  # src/model.py:58-60
 
 
+@gin_lite.configurable
 class MMTM_MVCNN(nn.Module):
     def __init__(self, nclasses=40, num_views=2, pretraining=False, mmtm_off=False,
                  mmtm_rescale_eval_file_path=None, mmtm_rescale_training_file_path=None, device='cuda:0',
