@@ -99,8 +99,6 @@ def run_flow(tmp_path, device, mmtm_cls=None):
         assert os.path.exists(os.path.join(paths["train"], f)), f
     rows = list(csv.DictReader(open(os.path.join(paths["train"], "history.csv"))))
     assert [int(r["epoch"]) for r in rows] == [1, 2, 3]
-    if guided:
-        assert "d_BDR" in rows[0] and "curation_mode" in rows[0]
     for key in ("loss", "acc", "acc_modal_0", "acc_modal_1", "val_loss", "val_acc", "test_acc", "time"):
         assert key in rows[0] and np.isfinite(float(rows[-1][key])), key
     hist = pickle.load(open(os.path.join(paths["train"], "history.pickle"), "rb"))
