@@ -275,8 +275,9 @@ class ReduceLROnPlateau_PyTorch(Callback):
         self.metric, self.factor, self.patience = metric, factor, patience
 
     def on_train_begin(self, logs):
+        optimizer = getattr(self.optimizer, "optimizer", self.optimizer)  # unwrap dist.DPOptimizer
         self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(
-            self.optimizer, mode='min', factor=self.factor, patience=self.patience, threshold=0.001,
+            optimizer, mode='min', factor=self.factor, patience=self.patience, threshold=0.001,
             threshold_mode='rel', cooldown=0, min_lr=1e-6, eps=1e-08)
 
     def on_epoch_end(self, epoch, logs):

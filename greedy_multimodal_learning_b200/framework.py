@@ -130,6 +130,11 @@ class StepIterator:
         self.losses_sum, self.sizes_sum = float(flat[0]), float(flat[1])
         self.metrics_sum = flat[2:2 + k].copy()
         self.metrics_permodal_sum = flat[2 + k:].reshape(self.metrics_permodal_sum.shape).copy()
+        if self.indices_list and self.indices_list[0] is not None:
+            # the utilization reader selects rows by `train_indices`: it needs every rank's
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, np.concatenate(self.indices_list, axis=0))
+            self.indices_list = [np.concatenate(parts, axis=0)]
 
     def __iter__(self):
         if self.steps_per_epoch is not None:

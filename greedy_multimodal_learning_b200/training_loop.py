@@ -18,6 +18,7 @@ from functools import partial
 import numpy as np
 import torch
 
+from . import dist as gdist
 from . import gin_lite
 from .callbacks import LambdaCallback, ModelCheckpoint, save_weights
 from .framework import Model_
@@ -73,6 +74,8 @@ def _device(use_gpu, device_numbers):
         return None
     if not torch.cuda.is_available():
         raise RuntimeError("use_gpu=True but no CUDA device is visible (this package has no CPU path)")
+    if gdist.world_size() > 1:  # one process per GPU: the launcher's LOCAL_RANK picks the device
+        return torch.device("cuda", torch.cuda.current_device())
     return torch.device("cuda:%d" % device_numbers[0])
 
 
@@ -86,15 +89,16 @@ def training_loop(model, loss_function, metrics, optimizer, config, save_path, s
     callbacks = list(custom_callbacks)
     # the reference passes `custom_callbacks` (a list) as `save_with_structure`, so the pickle is
     # written exactly when custom callbacks exist (src/training_loop.py:108-109); kept
-    callbacks += [
-        LambdaCallback(on_epoch_end=partial(_append_to_history, H=H)),
-        LambdaCallback(on_epoch_end=partial(_save_history, save_path=save_path, H=H,
-                                            save_with_structure=bool(custom_callbacks))),
-        ModelCheckpoint(monitor=checkpoint_monitor, save_best_only=True, mode='max',
-                        filepath=os.path.join(save_path, "model_best_val.pt")),
-        LambdaCallback(on_epoch_end=lambda epoch, logs: save_weights(
-            model, optimizer, os.path.join(save_path, "model_last_epoch.pt"))),
-    ]
+    callbacks.append(LambdaCallback(on_epoch_end=partial(_append_to_history, H=H)))
+    if gdist.rank() == 0:  # data parallel: replicas are identical, rank 0 owns the files
+        callbacks += [
+            LambdaCallback(on_epoch_end=partial(_save_history, save_path=save_path, H=H,
+                                                save_with_structure=bool(custom_callbacks))),
+            ModelCheckpoint(monitor=checkpoint_monitor, save_best_only=True, mode='max',
+                            filepath=os.path.join(save_path, "model_best_val.pt")),
+            LambdaCallback(on_epoch_end=lambda epoch, logs: save_weights(
+                model, optimizer, os.path.join(save_path, "model_last_epoch.pt"))),
+        ]
     _configure(callbacks, save_path, model, optimizer, config)
     engine = Model_(model=model, optimizer=optimizer, loss_function=loss_function, metrics=metrics, verbose=verbose,
                     nummodalities=nummodalities, data_parallel=data_parallel)

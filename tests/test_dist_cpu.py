@@ -175,3 +175,34 @@ def _random_ctl_worker(rank, world):
 def test_random_controller_is_rank_identical_under_shared_seed():
     a, b = _spawn(_random_ctl_worker)
     assert a == b and any(m for m, _ in a)
+
+
+def _train_cli_worker(rank, world):
+    """`train` entry point under a 2-process launch, oracle block plugged in (CPU has no product path)."""
+    import tempfile
+    from greedy_multimodal_learning_b200 import gin_lite
+    from greedy_multimodal_learning_b200.train import train
+    from oracle.mmtm_module import OracleMMTM
+    from tests import frontend_flow as ff
+    save = os.path.join(tempfile.gettempdir(), "gml_dp_cli_%s" % os.environ["MASTER_PORT"])
+    os.makedirs(save, exist_ok=True)
+    gin_lite.clear_config()
+    gin_lite.parse_config(ff.TRAIN % dict(use_gpu="False", callbacks="['CompletedStopping', 'ReduceLROnPlateau_PyTorch']"))
+    gin_lite.parse_config("training_loop.n_epochs=3\nget_mvdcndata.synthetic_samples=(20, 4)\n"
+                          "get_mvdcndata.image_size=32")
+    gin_lite.bind_parameter("MMTM_MVCNN.mmtm_cls", OracleMMTM)
+    H = train(save)
+    dist.barrier()
+    files = sorted(os.listdir(save))
+    ckpt = torch.load(os.path.join(save, "model_last_epoch.pt"), map_location="cpu")["model"]
+    return ({k: [float(x) for x in H[k]] for k in ("loss", "acc", "val_loss", "test_acc")},
+            [sorted(int(i) for i in e) for e in H["train_indices"]], files,
+            float(sum(v.double().sum() for v in ckpt.values())))
+
+
+def test_train_command_line_under_two_ranks():
+    (h0, idx0, files0, w0), (h1, idx1, files1, w1) = _spawn(_train_cli_worker)
+    assert h0 == h1                                   # epoch sums are all-reduced -> identical logs on every rank
+    assert idx0 == idx1 and len(idx0[0]) == 16 and len(set(idx0[0])) == 16  # 20 samples, valid_size 0.2
+    assert {"history.csv", "history.pickle", "model_best_val.pt", "model_last_epoch.pt"} <= set(files0)
+    assert w0 == w1 and np.isfinite(w0)
