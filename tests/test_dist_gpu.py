@@ -148,3 +148,32 @@ def test_guided_training_ranks_stay_in_lock_step():
     assert f0 == f1            # same statistic, same decisions on every rank, no extra collective
     assert w0 == w1            # replicas bit-identical after all-reduced updates
     assert any(c for c, _, _ in f0)
+
+
+def _train_cli_worker(rank, world):
+    """The reference's guided training command line, one process per GPU (product path, NCCL)."""
+    import tempfile
+    from greedy_multimodal_learning_b200 import gin_lite
+    from greedy_multimodal_learning_b200.train import train
+    from tests import frontend_flow as ff
+    save = os.path.join(tempfile.gettempdir(), "gml_dp_cli_%s" % os.environ["MASTER_PORT"])
+    os.makedirs(save, exist_ok=True)
+    gin_lite.clear_config()
+    gin_lite.parse_config(ff.TRAIN % dict(
+        use_gpu="True", callbacks="['CompletedStopping', 'ReduceLROnPlateau_PyTorch', 'Bias_Mitigation_Strong']"))
+    gin_lite.parse_config("train.batch_size=8\nget_mvdcndata.synthetic_samples=(40, 8)")
+    H = train(save)
+    dist.barrier()
+    ckpt = torch.load(os.path.join(save, "model_last_epoch.pt"), map_location="cpu")["model"]
+    return ({k: [float(x) for x in H[k]] for k in ("loss", "acc", "val_loss", "test_acc")},
+            [sorted(int(i) for i in e) for e in H["train_indices"]], sorted(os.listdir(save)),
+            float(sum(v.double().sum() for v in ckpt.values())), torch.cuda.current_device())
+
+
+def test_train_command_line_one_process_per_gpu():
+    (h0, idx0, files0, w0, d0), (h1, idx1, files1, w1, d1) = _spawn(_train_cli_worker)
+    assert (d0, d1) == (0, 1)
+    assert h0 == h1 and all(np.isfinite(v) for vs in h0.values() for v in vs)
+    assert idx0 == idx1 and len(idx0[0]) == 32 and len(set(idx0[0])) == 32
+    assert {"history.csv", "history.pickle", "model_best_val.pt", "model_last_epoch.pt"} <= set(files0)
+    assert w0 == w1
