@@ -56,6 +56,8 @@ SIGNATURES = {
                                         c_int32, _P, _P, _P, c_size_t, _P]),
     "gml_squeeze_accumulate": (c_int, [_P, _P, c_int32, c_int32, _P, _P, _P]),
     "gml_accuracy_counts": (c_int, [_P, _P, _P, c_int32, c_int32, _P, _P]),
+    "gml_fc_gemm_workspace_bytes": (c_size_t, []),
+    "gml_fc_gemm": (c_int, [_P, _P, _P, _P] + [c_int32] * 10 + [_P, c_size_t, _P]),
 }
 
 _lib = None

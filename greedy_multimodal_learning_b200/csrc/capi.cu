@@ -244,6 +244,10 @@ extern int g_fused_kind;
 extern int g_fused_prefetch;
 extern int g_fused_occ;
 extern int g_gemm_big_tiles;
+extern int g_gemm_tf32x3;
+extern int g_gemm_umma;
+extern int g_gemm_umma_dbg;
+extern long long* g_gemm_trace;
 extern int g_fused_weight_ratio_x100;
 extern int g_fused_group_kb;
 extern int g_fused_stash_kb;
@@ -264,6 +268,10 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "fused_stash_kb")) { g_fused_stash_kb = value < 0 ? 0 : (value > 200 ? 200 : (int)value); return GML_OK; }
   if (!strcmp(name, "fused_group_kb")) { g_fused_group_kb = (int)value; return GML_OK; }
   if (!strcmp(name, "gemm_big_tiles")) { g_gemm_big_tiles = value ? 1 : 0; return GML_OK; }
+  if (!strcmp(name, "gemm_tf32x3")) { g_gemm_tf32x3 = value ? 1 : 0; return GML_OK; }
+  if (!strcmp(name, "gemm_umma")) { g_gemm_umma = value ? 1 : 0; return GML_OK; }
+  if (!strcmp(name, "gemm_umma_dbg")) { g_gemm_umma_dbg = (int)value; return GML_OK; }
+  if (!strcmp(name, "gemm_trace_ptr")) { g_gemm_trace = reinterpret_cast<long long*>(value); return GML_OK; }
   if (!strcmp(name, "fused_occ")) {
     if (value != 4 && value != 5) return GML_E_BADARG;
     g_fused_occ = (int)value; return GML_OK;
@@ -530,4 +538,26 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
 
   if (!wgrad_done) GML_TRY(weight_grads(st, gws));
   return GML_OK;
+}
+
+// ---- the FC GEMM on its own (diagnostics, kernel tests, timing) -------------------------------
+extern "C" size_t gml_fc_gemm_workspace_bytes(void) { return gml::gemm_workspace_bytes(); }
+
+extern "C" int gml_fc_gemm(const float* a, const float* b, float* c, const float* bias, int32_t m, int32_t n, int32_t k,
+                           int32_t lda, int32_t ldb, int32_t ldc, int32_t a_kc, int32_t b_kc, int32_t act, int32_t beta,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace gml;
+  if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0 || ldc < n) return GML_E_BADARG;
+  if (lda < (a_kc ? k : m) || ldb < (b_kc ? k : n)) return GML_E_BADARG;
+  if (act < kActNone || act > kActSigmoid || (beta != 0 && beta != 1)) return GML_E_BADARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GemmDesc d{};
+  d.a = a; d.b = b; d.c = c; d.bias = bias; d.mask = nullptr;
+  d.m = m; d.n = n; d.k = k;
+  d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.ldmask = 0;
+  d.a_kc = a_kc ? 1 : 0; d.b_kc = b_kc ? 1 : 0;
+  d.act = act; d.beta = beta;
+  if (workspace && workspace_bytes < gemm_workspace_bytes()) return GML_E_WORKSPACE;
+  GML_TRY(prepare_gemm_workspace(workspace, workspace_bytes, st));
+  return launch_gemm(&d, 1, st, workspace, workspace_bytes);
 }

@@ -10,12 +10,22 @@
 // counter) adds the partials in split order -- a fixed order, so results are bit-reproducible --
 // and applies the epilogue (bias / ReLU / sigmoid / ReLU-mask / accumulate).
 // CUDA cores on purpose: 1e-5 fp32 parity with the reference's Linear layers (see fc_kernels.cu).
+#include <cooperative_groups.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace gml {
 
 int g_gemm_big_tiles = 0;  // tunable "gemm_big_tiles"
+int g_gemm_tf32x3 = 1;     // tunable "gemm_tf32x3": tensor-core 3xTF32 inner product (0 = CUDA-core FFMA)
+int g_gemm_umma = 1;       // tunable "gemm_umma": tcgen05 128x128 kernel for the large problems (0 = never)
+int g_gemm_umma_dbg = 0;   // experiment knob
+long long* g_gemm_trace = nullptr;  // debug: globaltimer stamps of CTA (0,0,0) of the tcgen05 kernel (device buffer, 64 slots)
 
 namespace {
 
@@ -34,6 +44,8 @@ struct PipeBatch {
   unsigned int* tickets; // [count][tiles_m * tiles_n]
   int splits;
   int k_per_split;       // multiple of BK
+  int dbg;
+  long long* trace;
 };
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int src_bytes) {
@@ -45,7 +57,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // one operand tile for k in [k0, k0 + BK): KC = k-contiguous source (src[t * ld + k]), else src[k * ld + t]
-template <bool KC, int BT>
+template <bool KC, int BT, int PITCH_MN = TileGeom<BT>::kPitchMN>
 __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ src, int ld, int t0, int tmax, int k0,
                                           int kmax, int tid) {
   constexpr int kChunks = BT * BK / 4;  // 16-byte chunks per tile
@@ -64,7 +76,7 @@ __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ sr
       int bytes = (k < kmax) ? (tmax - t) * 4 : 0;
       bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
       const float* g = bytes > 0 ? src + (size_t)k * ld + t : src;
-      cp_async16(s + kk * TileGeom<BT>::kPitchMN + tq, g, bytes);
+      cp_async16(s + kk * PITCH_MN + tq, g, bytes);
     }
   }
 }
@@ -94,6 +106,8 @@ __device__ __forceinline__ void frag(const float* s, int t_idx, int kk, float (&
       }
   }
 }
+
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ float epilogue(const GemmDesc& d, float v, int m, int n, const float* cp) {
   if (d.beta) v += *cp;
@@ -237,6 +251,581 @@ __global__ void __launch_bounds__(THREADS, TM == 4 ? 3 : 1) gemm_pipe_kernel(con
     }
   }
   if (tid == 0) *ticket = 0u;  // self-resetting: the workspace can be reused by the next launch
+}
+
+
+// -----------------------------------------------------------------------------------------------
+// Tensor-core variant of the 64x64 kernel: same cp.async pipeline, split-K and epilogue, the inner
+// product on mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = big + small, both TF32;
+// acc += small_a*big_b + big_a*small_b + big_a*big_b, fp32 accumulate).  The dropped small*small term is
+// ~2^-22 relative, i.e. the result stays at fp32 SGEMM accuracy (parity tests: 1e-5), while the FMA-pipe
+// ceiling of the CUDA-core kernel (~24 TFLOP/s, profiles/r1_experiments.md) no longer bounds the FC GEMMs.
+// Warp w owns rows 16*(w&3).. and columns 32*(w>>2).. of the tile: one A fragment, four B fragments,
+// 12 MMAs per k-step of 8.  [k][row] tiles use pitch 72 so that the fragment pattern (8t + g) is
+// bank-conflict-free; [row][k] tiles keep pitch 20 (20g + t is conflict-free as well).
+// -----------------------------------------------------------------------------------------------
+constexpr int MPITCH_MN = 64 + 8;
+constexpr int MMA_TILE_FLOATS = (64 * PITCH_KC > BK * MPITCH_MN) ? 64 * PITCH_KC : BK * MPITCH_MN;
+
+template <bool KC>
+__device__ __forceinline__ float tile_at(const float* s, int row, int k) {
+  return KC ? s[row * PITCH_KC + k] : s[k * MPITCH_MN + row];
+}
+// x = big + small with big = x truncated to TF32 (explicit mask) and small = x - big, which is exact in fp32.
+// `small` is handed to the tensor core as raw fp32 bits: the TF32 datapath reads only the top 19 bits, i.e.
+// truncates it, leaving a residual below 2^-21 |x|.  (cvt.rna.tf32.f32 is emulated with 4 instructions on
+// sm_100 -- 9 per split value; mask + subtract is 2.)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& small) {
+  big = __float_as_uint(x) & 0xffffe000u;
+  small = __float_as_uint(x - __uint_as_float(big));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(THREADS, 3) gemm_mma_kernel(const PipeBatch pb) {
+  constexpr int BM = 64, BN = 64;
+  extern __shared__ __align__(16) float gemm_smem[];
+  float (*As)[MMA_TILE_FLOATS] = reinterpret_cast<float (*)[MMA_TILE_FLOATS]>(gemm_smem);
+  float (*Bs)[MMA_TILE_FLOATS] = reinterpret_cast<float (*)[MMA_TILE_FLOATS]>(gemm_smem + STAGES * MMA_TILE_FLOATS);
+  __shared__ unsigned int s_ticket;
+  const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
+  const GemmDesc d = prob ? pb.d[1] : pb.d[0];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= d.m || n0 >= d.n) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  const int k_begin = split * pb.k_per_split;
+  const int k_end = min(d.k, k_begin + pb.k_per_split);
+  const int nk = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
+
+  // [n-tile j][c register]: row g + 8 (r >> 1), column 8 j + 2 t + (r & 1).  The tensor core adds into its
+  // accumulator with truncation, so `part` only ever holds ONE k-tile (16 k) and is then promoted into `acc`
+  // with a round-to-nearest add: the long sum over K behaves like the CUDA-core kernel's.
+  float acc[4][4], part[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) {
+      load_tile<A_KC, BM, MPITCH_MN>(As[s], d.a, d.lda, m0, d.m, k_begin + s * BK, k_end, tid);
+      load_tile<B_KC, BN, MPITCH_MN>(Bs[s], d.b, d.ldb, n0, d.n, k_begin + s * BK, k_end, tid);
+    }
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int nxt = kt + STAGES - 1;
+    if (nxt < nk) {
+      load_tile<A_KC, BM, MPITCH_MN>(As[nxt % STAGES], d.a, d.lda, m0, d.m, k_begin + nxt * BK, k_end, tid);
+      load_tile<B_KC, BN, MPITCH_MN>(Bs[nxt % STAGES], d.b, d.ldb, n0, d.n, k_begin + nxt * BK, k_end, tid);
+    }
+    cp_async_commit();
+    const float* as = As[kt % STAGES];
+    const float* bs = Bs[kt % STAGES];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) part[j][r] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 8) {
+      uint32_t a_big[4], a_small[4];
+      split_tf32(tile_at<A_KC>(as, wm + g, kk + t), a_big[0], a_small[0]);
+      split_tf32(tile_at<A_KC>(as, wm + g + 8, kk + t), a_big[1], a_small[1]);
+      split_tf32(tile_at<A_KC>(as, wm + g, kk + t + 4), a_big[2], a_small[2]);
+      split_tf32(tile_at<A_KC>(as, wm + g + 8, kk + t + 4), a_big[3], a_small[3]);
+      uint32_t b_big[4][2], b_small[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        split_tf32(tile_at<B_KC>(bs, wn + 8 * j + g, kk + t), b_big[j][0], b_small[j][0]);
+        split_tf32(tile_at<B_KC>(bs, wn + 8 * j + g, kk + t + 4), b_big[j][1], b_small[j][1]);
+      }
+      // correction terms first, then the leading term; four independent accumulator chains per pass
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_tf32(part[j], a_small, b_big[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_tf32(part[j], a_big, b_small[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_tf32(part[j], a_big, b_big[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[j][r] += part[j][r];
+  }
+  cp_async_wait<0>();
+
+  auto row_of = [&](int r) { return m0 + wm + g + 8 * (r >> 1); };
+  auto col_of = [&](int j, int r) { return n0 + wn + 8 * j + 2 * t + (r & 1); };
+
+  if (pb.splits == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int m = row_of(r), n = col_of(j, r);
+        if (m >= d.m || n >= d.n) continue;
+        float* cp = d.c + (size_t)m * d.ldc + n;
+        *cp = epilogue(d, acc[j][r], m, n, cp);
+      }
+    return;
+  }
+  float* partials = pb.part[prob];
+  const size_t plane = (size_t)d.m * d.n;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = row_of(r), n = col_of(j, r);
+      if (m < d.m && n < d.n) __stcg(partials + (size_t)split * plane + (size_t)m * d.n + n, acc[j][r]);
+    }
+  __threadfence();
+  __syncthreads();
+  unsigned int* ticket = pb.tickets + (size_t)prob * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x;
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)pb.splits - 1) return;
+  __threadfence();
+  // last CTA of the tile: fold the partials in split order (fixed order -> reproducible), 16 loads in flight
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
+  for (int sp = 0; sp < pb.splits; ++sp) {
+    float v[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int m = row_of(r), n = col_of(j, r);
+        v[j][r] = (m < d.m && n < d.n) ? __ldcg(partials + (size_t)sp * plane + (size_t)m * d.n + n) : 0.f;
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[j][r] += v[j][r];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = row_of(r), n = col_of(j, r);
+      if (m >= d.m || n >= d.n) continue;
+      float* cp = d.c + (size_t)m * d.ldc + n;
+      *cp = epilogue(d, acc[j][r], m, n, cp);
+    }
+  if (tid == 0) *ticket = 0u;
+}
+
+
+// -----------------------------------------------------------------------------------------------
+// tcgen05 (UMMA) kernel for the large FC problems: 128x128 output tile per CTA, accumulators in TMEM,
+// operands in shared memory in the canonical K-major SWIZZLE_128B UMMA layout, MMAs issued by one thread.
+//
+// fp32 accuracy from TF32 tensor cores (3xTF32): every operand element is split once, in shared memory, into
+// big = x & ~0x1fff (exactly a TF32 number) and small = x - big (exact in fp32; the TF32 datapath reads its
+// top 19 bits); per k-step of 8 the issuing thread queues small_a*big_b, big_a*small_b, big_a*big_b into the
+// same TMEM accumulator.  The tensor core adds into its accumulator with truncation, so a chain is kept short:
+// the K loop runs in groups of 128 k that alternate between two TMEM accumulators; while one group is being
+// multiplied the previous one is drained (tcgen05.ld) into per-thread fp32 sums with round-to-nearest adds.
+//
+// Roles (9 warps): warps 0-7 load (cp.async, 16-byte chunks), split, drain and run the epilogue; warp 8 issues
+// the MMAs.  Hand-offs are mbarriers: full[s] (256 producer arrivals) -> MMA; empty[s] (tcgen05.commit) ->
+// producers; acc_full[b] (tcgen05.commit) -> drainers; acc_empty[b] (256 arrivals) -> MMA.
+//
+// Shared-memory operand tile (128 rows x 32 k, 16 KB): an atom is 8 rows of 128 bytes on a 1024-byte boundary;
+// the 16-byte chunk kc of row t sits at 1024 (t / 8) + 128 (t % 8) + 16 (kc ^ (t % 8)) -- the XOR swizzle the
+// tensor core undoes.  Descriptor per k-step j: start + 32 j, SBO (8-row group stride) = 1024.
+//   * K-major source (src[t * ld + k]): cp.async writes each chunk straight to its final place; the thread
+//     that loaded it rewrites it as big in place and writes small to the twin tile.
+//   * MN-major source (src[k * ld + t]; the tcgen05 transpose path returned zeros for TF32 here): a chunk is
+//     4 t of one k.  It lands in a thread-private slot, is read back to registers, transposed 4x4 across the
+//     four lanes that hold k..k+3 (two shuffle rounds) into K-major chunks, split and stored.
+// Every lane group of 8 touches 8 different bank groups and every global read is a 64-byte run.
+// -----------------------------------------------------------------------------------------------
+constexpr int UM = 128, UN = 128, UK = 32, USTAGES = 3, UGROUP = 4;
+constexpr int U_PRODUCERS = 256, UTHREADS = U_PRODUCERS + 32;
+constexpr int U_TILE_BYTES = UM * UK * 4;        // 16 KB
+constexpr int U_STAGE_BYTES = 4 * U_TILE_BYTES;  // A big | A small | B big | B small
+constexpr uint32_t U_TMEM_COLS = 256;            // two accumulators of 128 lanes x 128 fp32 columns
+
+__device__ __forceinline__ uint32_t u_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void u_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(u_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void u_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {  // bounded: a lost completion must trap, never hang the GPU
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(u_smem_addr(bar)), "r"(parity)
+        : "memory");
+    if (!ok && spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void u_commit(uint64_t* bar) {
+  // arrives on the barrier once every MMA this thread has issued so far is complete
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint64_t u_desc(uint32_t addr) {
+  // start address [0,14) >> 4; leading byte offset [16,30) unused for swizzled K-major (1); stride byte offset
+  // [32,46) = 1024 >> 4; descriptor version 1 at [46,48); layout type SWIZZLE_128B (2) at [61,64)
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void u_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void u_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of chunk kc of row t in the swizzled K-major tile
+__device__ __forceinline__ uint32_t u_kmajor_off(int t, int kc) {
+  return (uint32_t)((t >> 3) * 1024 + (t & 7) * 128 + ((kc ^ (t & 7)) << 4));
+}
+constexpr int U_MN_PITCH = UM + 4;  // floats per k row of an MN-major landing zone (16-byte aligned rows; a column
+                                    // walk of 4 k then touches banks 4 apart -> conflict-free with the lane map below)
+// K-major source: chunk i of a producer thread is row t, k-chunk kc; it lands at its final (swizzled) offset.
+template <bool KC>
+__device__ __forceinline__ void u_chunk(int i, int warp, int lane, int& t, int& kc) {
+  const int wc = warp + 8 * i;
+  if (KC) {  // 8 rows x 4 k-chunks per warp: 64-byte global runs, one swizzle atom row group per 8 lanes
+    kc = (wc >> 4) * 4 + (lane >> 3);
+    t = (wc & 15) * 8 + (lane & 7);
+  } else {   // final chunks of an MN-major source: 16 rows x 2 k-chunks per warp (see u_read_chunks)
+    kc = (wc >> 3) * 2 + (lane >> 4);
+    t = (wc & 7) * 16 + (lane & 15);
+  }
+}
+template <bool KC>
+__device__ __forceinline__ void u_load_tile(unsigned char* tile, const float* __restrict__ src, int ld, int t0, int tmax,
+                                            int k0, int kmax, int warp, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int bytes;
+    const float* g;
+    uint32_t land;
+    if (KC) {
+      int t, kc;
+      u_chunk<true>(i, warp, lane, t, kc);
+      land = u_kmajor_off(t, kc);
+      t += t0;
+      const int k = k0 + kc * 4;
+      bytes = (t < tmax) ? (kmax - k) * 4 : 0;
+      g = src + (size_t)t * ld + k;
+    } else {  // k row `kr`, 4 consecutive t: one warp covers a whole 512-byte row of the tile
+      const int kr = warp + 8 * i, tc = lane;
+      land = (uint32_t)((kr * U_MN_PITCH + tc * 4) * 4);
+      const int k = k0 + kr, t = t0 + tc * 4;
+      bytes = (k < kmax) ? (tmax - t) * 4 : 0;
+      g = src + (size_t)k * ld + t;
+    }
+    bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+    cp_async16(reinterpret_cast<float*>(tile + land), bytes > 0 ? g : src, bytes);
+  }
+}
+// K-major: my own chunks back from where cp.async put them.  MN-major: the landing zone holds [k][t]; chunk
+// (t, kc) is the column walk k = 4 kc .. 4 kc + 3 at fixed t -- 16 lanes on 16 consecutive t, the two lane halves
+// 4 k rows (16 banks) apart: conflict-free.  (Needs a barrier first: other threads loaded those rows.)
+template <bool KC>
+__device__ __forceinline__ void u_read_chunks(const unsigned char* tile, int warp, int lane, float4 (&x)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int t, kc;
+    u_chunk<KC>(i, warp, lane, t, kc);
+    if (KC) {
+      x[i] = *reinterpret_cast<const float4*>(tile + u_kmajor_off(t, kc));
+    } else {
+      const float* col = reinterpret_cast<const float*>(tile) + (kc * 4) * U_MN_PITCH + t;
+      x[i] = make_float4(col[0], col[U_MN_PITCH], col[2 * U_MN_PITCH], col[3 * U_MN_PITCH]);
+    }
+  }
+}
+// big (in place for K-major sources, where the raw chunk already sits at its final offset and the tensor core
+// reads only the top 19 bits of each word, i.e. sees exactly x & ~0x1fff) and small = x - big (twin tile)
+template <bool KC>
+__device__ __forceinline__ void u_write_split(unsigned char* big_tile, unsigned char* small_tile, int warp, int lane,
+                                              const float4 (&x)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int t, kc;
+    u_chunk<KC>(i, warp, lane, t, kc);
+    const uint32_t fin = u_kmajor_off(t, kc);
+    const float4 v = x[i];
+    float4 b, s;
+    b.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); s.x = v.x - b.x;
+    b.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); s.y = v.y - b.y;
+    b.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); s.z = v.z - b.z;
+    b.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); s.w = v.w - b.w;
+    if (!KC) *reinterpret_cast<float4*>(big_tile + fin) = b;
+    *reinterpret_cast<float4*>(small_tile + fin) = s;
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(UTHREADS, 1) gemm_umma_kernel(const PipeBatch pb) {
+  extern __shared__ __align__(1024) unsigned char u_smem_raw[];
+  // swizzle atoms must sit on 1024-byte boundaries of the shared-memory address space
+  unsigned char* u_smem = u_smem_raw + ((1024u - (u_smem_addr(u_smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bar_full[USTAGES], bar_empty[USTAGES], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint32_t s_tmem;
+    const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
+  const GemmDesc d = prob ? pb.d[1] : pb.d[0];
+  const int m0 = blockIdx.y * UM, n0 = blockIdx.x * UN;
+  if (m0 >= d.m || n0 >= d.n) return;  // uniform for the CTA, before anything is allocated
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k_begin = split * pb.k_per_split;
+  const int k_end = min(d.k, k_begin + pb.k_per_split);
+  const int nk = k_end > k_begin ? (k_end - k_begin + UK - 1) / UK : 0;
+  const int ngroups = (nk + UGROUP - 1) / UGROUP;
+  const bool tracing = pb.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define U_STAMP(i)                                                      \
+  do {                                                                  \
+    if (tracing) {                                                      \
+      long long t_;                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));            \
+      pb.trace[(i)] = t_;                                               \
+    }                                                                   \
+  } while (0)
+  U_STAMP(0);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < USTAGES; ++s) {
+      u_mbar_init(&bar_full[s], U_PRODUCERS);
+      u_mbar_init(&bar_empty[s], 1);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      u_mbar_init(&bar_acc_full[b], 1);
+      u_mbar_init(&bar_acc_empty[b], U_PRODUCERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(u_smem_addr(&s_tmem)),
+                 "r"(U_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  U_STAMP(1);
+
+  float sum[64];  // producers: row 32 (warp & 3) + lane, columns 64 (warp >> 2) .. + 63 of the tile
+#pragma unroll
+  for (int i = 0; i < 64; ++i) sum[i] = 0.f;
+
+  if (warp == U_PRODUCERS / 32) {
+    // ===== MMA issuer =====================================================================
+    if (lane == 0) {
+      // instruction descriptor: D fp32 [4,6)=1, A and B TF32 [7,10)=[10,13)=2, both K-major, N >> 3 at [17,23),
+      // M >> 4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+      for (int kt = 0; kt < nk; ++kt) {
+        const int stage = kt % USTAGES, g = kt / UGROUP, b = g & 1;
+        if (kt % UGROUP == 0 && g >= 2) u_mbar_wait(&bar_acc_empty[b], (uint32_t)(((g >> 1) - 1) & 1));
+        u_mbar_wait(&bar_full[stage], (uint32_t)((kt / USTAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_big = u_smem_addr(u_smem + stage * U_STAGE_BYTES), a_small = a_big + U_TILE_BYTES;
+        const uint32_t b_big = a_big + 2 * U_TILE_BYTES, b_small = a_big + 3 * U_TILE_BYTES;
+        const uint32_t acc = tmem + (uint32_t)(b * UN);
+#pragma unroll
+        for (int j = 0; j < UK / 8; ++j) {
+          const uint32_t o = (uint32_t)j * 32u;  // 8 k further inside the 128-byte rows
+          const uint64_t da_b = u_desc(a_big + o), da_s = u_desc(a_small + o);
+          const uint64_t db_b = u_desc(b_big + o), db_s = u_desc(b_small + o);
+          u_mma_tf32(acc, da_s, db_b, idesc, (kt % UGROUP != 0 || j != 0) ? 1u : 0u);
+          u_mma_tf32(acc, da_b, db_s, idesc, 1u);
+          u_mma_tf32(acc, da_b, db_b, idesc, 1u);
+        }
+        u_commit(&bar_empty[stage]);
+        if (kt % UGROUP == UGROUP - 1 || kt == nk - 1) u_commit(&bar_acc_full[b]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== producers / drainers ===========================================================
+    const uint32_t t_row = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 64);
+    int drained = 0;
+    auto drain = [&](int gi) {
+      const int b = gi & 1;
+      u_mbar_wait(&bar_acc_full[b], (uint32_t)((gi >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v[16];
+        u_tmem_ld16(t_row + (uint32_t)(b * UN + 16 * c), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum[16 * c + i] += v[i];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      u_mbar_arrive(&bar_acc_empty[b]);
+    };
+    auto issue_loads = [&](int kt) {
+      unsigned char* st = u_smem + (kt % USTAGES) * U_STAGE_BYTES;
+      const int k0 = k_begin + kt * UK;
+      u_load_tile<A_KC>(st, d.a, d.lda, m0, d.m, k0, k_end, warp, lane);
+      u_load_tile<B_KC>(st + 2 * U_TILE_BYTES, d.b, d.ldb, n0, d.n, k0, k_end, warp, lane);
+    };
+#pragma unroll
+    for (int s = 0; s < USTAGES - 1; ++s) {
+      if (s < nk) issue_loads(s);
+      cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+      const int nxt = kt + USTAGES - 1;
+      if (nxt < nk) {
+        // tile nxt reuses the stage of tile nxt - USTAGES: wait until the MMAs that read it are done
+        if (nxt >= USTAGES) u_mbar_wait(&bar_empty[nxt % USTAGES], (uint32_t)(((nxt / USTAGES) - 1) & 1));
+        issue_loads(nxt);
+      }
+      cp_async_commit();
+      cp_async_wait<USTAGES - 1>();  // my chunks of tile kt have landed
+      if (kt < 8) U_STAMP(2 + 4 * kt);
+      unsigned char* st = u_smem + (kt % USTAGES) * U_STAGE_BYTES;
+      float4 xa[4], xb[4];
+      if (!A_KC || !B_KC) asm volatile("bar.sync 1, 256;" ::: "memory");  // every producer's rows of tile kt are in
+      u_read_chunks<A_KC>(st, warp, lane, xa);
+      u_read_chunks<B_KC>(st + 2 * U_TILE_BYTES, warp, lane, xb);
+      if (!A_KC || !B_KC) asm volatile("bar.sync 1, 256;" ::: "memory");  // ... and read, before the zone is rewritten
+      u_write_split<A_KC>(st, st + U_TILE_BYTES, warp, lane, xa);
+      u_write_split<B_KC>(st + 2 * U_TILE_BYTES, st + 3 * U_TILE_BYTES, warp, lane, xb);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA unit
+      u_mbar_arrive(&bar_full[kt % USTAGES]);
+      if (kt < 8) U_STAMP(3 + 4 * kt);
+      // drain a finished group once the MMA warp has the next group's first tile to chew on
+      if (kt % UGROUP >= 1 && drained < kt / UGROUP) { drain(drained); ++drained; }
+      if (kt < 8) U_STAMP(4 + 4 * kt);
+    }
+    cp_async_wait<0>();
+    U_STAMP(40);
+    while (drained < ngroups) { drain(drained); ++drained; }
+    U_STAMP(41);
+  }
+
+  // ---- epilogue ------------------------------------------------------------------------------------------
+  // Each producer thread holds one row x 64 columns of this CTA's partial tile.  Without split-K it is written
+  // out directly.  With split-K the CTAs of a tile form a thread-block cluster (along z): every CTA parks its
+  // partial tile in its own shared memory, and after a cluster barrier CTA r adds up -- in split order, so the
+  // result is reproducible -- and stores a contiguous column range of the tile, reading the other CTAs' partials
+  // over distributed shared memory.  No global partials, no tickets, no fences.
+  const bool worker = warp < U_PRODUCERS / 32;
+  const int row = 32 * (warp & 3) + lane;
+  const int col0 = (warp >> 2) * 64;
+  const bool vec_c = (d.ldc & 3) == 0 && aligned16_dev(d.c);
+
+  auto store4 = [&](float4 v, int m, int n) {  // epilogue + store of columns n..n+3 of row m
+    float* crow = d.c + (size_t)m * d.ldc;
+    if (vec_c && n + 3 < d.n) {
+      float4 o, old = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (d.beta) old = *reinterpret_cast<const float4*>(crow + n);
+      o.x = epilogue(d, v.x, m, n + 0, &old.x);
+      o.y = epilogue(d, v.y, m, n + 1, &old.y);
+      o.z = epilogue(d, v.z, m, n + 2, &old.z);
+      o.w = epilogue(d, v.w, m, n + 3, &old.w);
+      *reinterpret_cast<float4*>(crow + n) = o;
+    } else {
+      const float e4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < d.n) crow[n + e] = epilogue(d, e4[e], m, n + e, crow + n + e);
+    }
+  };
+
+  if (pb.splits == 1) {
+    if (worker && m0 + row < d.m) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int n = n0 + col0 + 4 * c;
+        if (n < d.n) store4(make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]), m0 + row, n);
+      }
+    }
+  } else {
+    cg::cluster_group cluster = cg::this_cluster();
+    // partial tile as [32 column chunks][129 rows] float4 (pitch 129: chunk-fastest readers stay conflict-free);
+    // the operand stages are free: every MMA of this CTA has completed (all groups drained)
+    float4* red = reinterpret_cast<float4*>(u_smem);
+    constexpr int RED_PITCH = 129;
+    __syncthreads();
+    if (worker) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        red[(col0 / 4 + c) * RED_PITCH + row] = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
+    }
+    U_STAMP(42);
+    cluster.sync();
+    U_STAMP(43);
+    // 128 rows x (32 / splits) column chunks per CTA = 16 / splits items per thread; all 16 remote loads of a
+    // thread are issued before the first add
+    if (worker) {
+      auto reduce = [&](auto splits_tag) {
+        constexpr int SP = decltype(splits_tag)::value, CPC = 32 / SP, ITEMS = 128 * CPC / U_PRODUCERS;
+        float4 v[ITEMS][SP];
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+          const int item = tid + it * U_PRODUCERS, chunk = split * CPC + item % CPC, r = item / CPC;
+#pragma unroll
+          for (int sp = 0; sp < SP; ++sp) v[it][sp] = cluster.map_shared_rank(red, sp)[chunk * RED_PITCH + r];
+        }
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+          const int item = tid + it * U_PRODUCERS, chunk = split * CPC + item % CPC, r = item / CPC;
+          float4 acc = v[it][0];
+#pragma unroll
+          for (int sp = 1; sp < SP; ++sp) { acc.x += v[it][sp].x; acc.y += v[it][sp].y; acc.z += v[it][sp].z; acc.w += v[it][sp].w; }
+          const int m = m0 + r, n = n0 + 4 * chunk;
+          if (m < d.m && n < d.n) store4(acc, m, n);
+        }
+      };
+      if (pb.splits == 2) reduce(std::integral_constant<int, 2>{});
+      else if (pb.splits == 4) reduce(std::integral_constant<int, 4>{});
+      else reduce(std::integral_constant<int, 8>{});
+    }
+    cluster.sync();  // nobody leaves while a neighbour may still be reading its partial tile
+  }
+  U_STAMP(44);
+  // every warp is done with its tcgen05.ld before the columns go back to the allocator
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(U_TMEM_COLS) : "memory");
+  }
+  U_STAMP(45);
+#undef U_STAMP
 }
 
 
@@ -440,27 +1029,41 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   // 128x128 tiles (gemm_big_kernel, 8x8 outputs per thread) measured SLOWER than the 64x64 cp.async kernel at
   // 3 CTAs per SM on every FC shape of the three blocks (profiles/r1_experiments.md), so they are opt-in only.
   const bool big = g_gemm_big_tiles && (long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * count >= 24 && min_k >= 64;
-  const int BM = big ? 128 : 64, BN = BM;
+  // tcgen05 kernel: worth its fixed costs (TMEM allocation, 192 KB of shared memory, one CTA per SM) only for the
+  // big FC problems (batch >= ~512 on the 256- and 512-channel blocks)
+  const bool umma = g_gemm_umma && !big && min_k >= 256 && (long)max_m * max_n >= 128L * 512 && max_m >= 128 &&
+                    max_n >= 128;
+  const int BM = (big || umma) ? 128 : 64, BN = BM;
+  const int bk = umma ? UK : BK;
   const int tiles_m = ceil_div(max_m, BM), tiles_n = ceil_div(max_n, BN);
   const long tiles = (long)tiles_m * tiles_n * count;
-  const int nk = ceil_div(min_k, BK);
-  int splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
-  if (splits > nk / 4) splits = nk / 4;  // at least 4 k-tiles per split
+  const int nk = ceil_div(min_k, bk);
+  // tcgen05 kernel: one CTA per SM (shared memory), so the grid must fit ONE wave: splits = floor(SMs / tiles)
+  int splits = umma ? (int)(kNumSMs / tiles) : (int)((2 * kNumSMs + tiles - 1) / tiles);
+  const int min_tiles_per_split = umma ? 2 : 4;
+  if (splits > nk / min_tiles_per_split) splits = nk / min_tiles_per_split;
   if (splits > 16) splits = 16;
   if (splits < 1) splits = 1;
+  if (umma) {  // the splits of a tile form one thread-block cluster: 1, 2, 4 or 8
+    int p2 = 1;
+    while (p2 * 2 <= splits && p2 < 8) p2 *= 2;
+    splits = p2;
+  }
   const size_t ticket_bytes = 65536;  // fixed-size ticket block at the head of the workspace
   if ((size_t)tiles * sizeof(unsigned int) > ticket_bytes) return GML_E_UNSUPPORTED;
-  while (splits > 1) {
+  while (splits > 1 && !umma) {
     size_t need = ticket_bytes;
     for (int i = 0; i < count; ++i) need += round_up((size_t)splits * descs[i].m * descs[i].n * sizeof(float), 256);
     if (ws && need <= ws_bytes) break;
     --splits;
   }
   pb.splits = splits;
-  pb.k_per_split = ceil_div(nk, splits) * BK;
+  pb.dbg = g_gemm_umma_dbg;
+  pb.trace = g_gemm_trace;
+  pb.k_per_split = ceil_div(nk, splits) * bk;
   pb.tickets = nullptr;
   pb.part[0] = pb.part[1] = nullptr;
-  if (splits > 1) {
+  if (splits > 1 && !umma) {
     char* p = static_cast<char*>(ws);
     pb.tickets = reinterpret_cast<unsigned int*>(p);
     p += ticket_bytes;
@@ -476,8 +1079,26 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
     const bool akc = descs[0].a_kc != 0, bkc = descs[0].b_kc != 0;
 #define GML_GEMM(AK, BKC)                                                                                   \
   do {                                                                                                      \
-    if (big) {                                                                                              \
+    if (umma) {                                                                                             \
+      static bool attr_set = false;                                                                         \
+      const size_t sm = (size_t)USTAGES * U_STAGE_BYTES + 1024;                                                   \
+      if (!attr_set) {                                                                                      \
+        GML_CUDA_TRY(cudaFuncSetAttribute(gemm_umma_kernel<AK, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)sm));                                                        \
+        attr_set = true;                                                                                    \
+      }                                                                                                     \
+      cudaLaunchConfig_t cfg = {};                                                                          \
+      cfg.gridDim = grid; cfg.blockDim = dim3(UTHREADS); cfg.dynamicSmemBytes = sm; cfg.stream = st;         \
+      cudaLaunchAttribute attr[1];                                                                          \
+      attr[0].id = cudaLaunchAttributeClusterDimension;                                                     \
+      attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = splits;         \
+      cfg.attrs = attr; cfg.numAttrs = 1;                                                                   \
+      GML_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<AK, BKC>, pb));                                 \
+    } else if (big) {                                                                                       \
       gemm_big_kernel<AK, BKC><<<grid, THREADS, 0, st>>>(pb);                                                \
+    } else if (g_gemm_tf32x3) {                                                                             \
+      const size_t sm = 2 * STAGES * MMA_TILE_FLOATS * sizeof(float);                                        \
+      gemm_mma_kernel<AK, BKC><<<grid, THREADS, sm, st>>>(pb);                                               \
     } else {                                                                                                \
       const size_t sm = 2 * STAGES * TileGeom<64>::kFloats * sizeof(float);                                  \
       gemm_pipe_kernel<AK, BKC, 4><<<grid, THREADS, sm, st>>>(pb);                                           \

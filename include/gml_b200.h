@@ -215,6 +215,22 @@ int gml_squeeze_accumulate(const float* s, const uint8_t* select, int32_t n, int
 int gml_accuracy_counts(const float* logits0, const float* logits1, const int64_t* labels,
                         int32_t n, int32_t k, int32_t* counts3, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * The FC building block on its own (what torch.nn.Linear / AddmmBackward0 do inside
+ * src/balanced_mmtm.py:101-108 and its autograd graph); exported so that the GEMM kernels
+ * (CUDA-core, mma.sync 3xTF32, tcgen05 3xTF32 -- see gml_set_tunable) can be tested and timed
+ * in isolation:
+ *     C[i, j] = act(beta * C[i, j] + sum_k A(i, k) * B(j, k) + bias[j])
+ * A(i, k) = a[i * lda + k] when a_kc != 0, else a[k * lda + i]; same for B with b_kc / ldb.
+ * act: 0 none, 1 ReLU, 2 sigmoid.  workspace: gml_fc_gemm_workspace_bytes() bytes (split-K
+ * partials and tickets); may be NULL (no split-K, generic kernel).
+ */
+size_t gml_fc_gemm_workspace_bytes(void);
+int gml_fc_gemm(const float* a, const float* b, float* c, const float* bias,
+                int32_t m, int32_t n, int32_t k, int32_t lda, int32_t ldb, int32_t ldc,
+                int32_t a_kc, int32_t b_kc, int32_t act, int32_t beta,
+                void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

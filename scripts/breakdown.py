@@ -37,7 +37,7 @@ for c, h in SHAPES:
                                           b.ws_bytes, b.dims, 0, 1.0, fl, st)
         for name in args.variants.split(","):
             flags, tun = VARIANTS[name]
-            for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "gemm_big_tiles": 0, **tun}.items():
+            for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "gemm_big_tiles": 0, "gemm_tf32x3": 1, "gemm_umma": 1, **tun}.items():
                 L.check(lib.gml_set_tunable(k.encode(), v))
             if fwd(flags) == -5:
                 continue

@@ -22,6 +22,9 @@ VARIANTS = {
     # name: (flags, tunables)
     "auto": (0, {}),
     "auto_biggemm": (0, {"gemm_big_tiles": 1}),
+    "auto_ffma": (0, {"gemm_tf32x3": 0, "gemm_umma": 0}),
+    "auto_mmasync": (0, {"gemm_umma": 0}),
+    "stream_ffma": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 100000, "gemm_tf32x3": 0, "gemm_umma": 0}),
     "stream_c40": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 40}),
     "stream_c64": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 64}),
     "stream_c100": (L.F_FORCE_STREAMING, {"l2_chunk_mb": 100}),
@@ -87,7 +90,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 rc = fwd(flags)
                 if rc == -5:

@@ -13,7 +13,7 @@ import greedy_multimodal_learning_b200 as pkg
 from greedy_multimodal_learning_b200 import _lib
 from oracle import mmtm_oracle as mo
 from tests.golden import make_golden_cases as cases
-from tests.helpers import assert_close, rel_err
+from tests.helpers import assert_close, rel_err, relu_ambiguous_samples
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -154,6 +154,11 @@ def test_oracle_parity_odd_shapes(shape, mode, path):
     warm = dict(A=t(2, c_v, h_v, w_v), B=t(2, c_s, h_s, w_s))
     p = mo.synth_params(5, c_v, c_s)
     avg = [0.1 * t(c_v), 0.1 * t(c_s)]
+    if n > 1000:  # > 1e6 hidden units: some pre-activations sit inside fp32 noise of zero (see helper)
+        amb = relu_ambiguous_samples(x, p, mode, avg)
+        assert amb.sum() < 40
+        x["gA"][amb] = 0
+        x["gB"][amb] = 0
     m = make_module(c_v, c_s, p, PATHS[path])
     r = run_cuda(m, x, mode, avg, warm)
     st = mo.MMTMState.zeros(c_v)
