@@ -1031,8 +1031,11 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   const bool big = g_gemm_big_tiles && (long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * count >= 24 && min_k >= 64;
   // tcgen05 kernel: worth its fixed costs (TMEM allocation, 192 KB of shared memory, one CTA per SM) only for the
   // big FC problems (batch >= ~512 on the 256- and 512-channel blocks)
-  const bool umma = g_gemm_umma && !big && min_k >= 256 && (long)max_m * max_n >= 128L * 512 && max_m >= 128 &&
-                    max_n >= 128;
+  // tensor cores only pay off on the large problems (measured cross-over, scripts/gemm_accuracy.py); everything
+  // smaller stays on the CUDA-core kernel
+  const bool large = (double)max_m * max_n * min_k * count >= 1e8;
+  const bool umma = g_gemm_umma && !big && large && min_k >= 256 && max_m >= 128 && max_n >= 128;
+  const bool mma_sync = g_gemm_tf32x3 && large;
   const int BM = (big || umma) ? 128 : 64, BN = BM;
   const int bk = umma ? UK : BK;
   const int tiles_m = ceil_div(max_m, BM), tiles_n = ceil_div(max_n, BN);
@@ -1096,7 +1099,7 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
       GML_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<AK, BKC>, pb));                                 \
     } else if (big) {                                                                                       \
       gemm_big_kernel<AK, BKC><<<grid, THREADS, 0, st>>>(pb);                                                \
-    } else if (g_gemm_tf32x3) {                                                                             \
+    } else if (mma_sync) {                                                                                  \
       const size_t sm = 2 * STAGES * MMA_TILE_FLOATS * sizeof(float);                                        \
       gemm_mma_kernel<AK, BKC><<<grid, THREADS, sm, st>>>(pb);                                               \
     } else {                                                                                                \
