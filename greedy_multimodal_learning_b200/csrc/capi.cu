@@ -354,7 +354,7 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
   const bool can_fuse = !(flags & GML_F_FORCE_STREAMING) && !curate &&
                         fused_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
   if ((flags & GML_F_FORCE_FUSED) && !can_fuse) return GML_E_UNSUPPORTED;
-  if (can_fuse) {
+  if (can_fuse && ((flags & GML_F_FORCE_FUSED) || fused_fwd_preferred(d.n, d.c_v, d.hw_v, d.d))) {
     FusedFwdArgs fa{a, b, a_out, b_out, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, run_v, run_s,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
     GML_TRY(launch_fused_fwd(fa, st));

@@ -1154,6 +1154,17 @@ bool fused_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mod
   return pick_cfg(n, c_v, hw_v, d, &fb, &l2, true) && weights_ok(fb);
 }
 
+// Forward only: at large batch the batched FC GEMMs (tcgen05) get cheap, while the cluster kernel re-reads the FC
+// weights from L2 once per group.  Measured on B200 (profiles/r1_sweep.md): 256x14^2 at batch 1024 runs 0.297 ms
+// streaming vs 0.321 ms fused; 128x28^2 (weights 16 % of a group) stays fused at every batch.
+bool fused_fwd_preferred(int n, int c, int hw, int d) {
+  FusedCfg f;
+  bool l2 = false;
+  if (!pick_cfg(n, c, hw, d, &f, &l2, false)) return false;
+  const double w_bytes = 16.0 * f.c * f.d, group_bytes = 2.0 * f.g * 2.0 * f.c * f.hw * 4.0;
+  return !(n >= 1024 && w_bytes > 0.5 * group_bytes);
+}
+
 int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st) {
   FusedCfg f;
   bool l2 = false;

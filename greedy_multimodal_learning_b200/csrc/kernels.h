@@ -107,6 +107,7 @@ struct FusedBwdArgs {
   float gate_scale;
 };
 bool fused_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mode);
+bool fused_fwd_preferred(int n, int c, int hw, int d);
 int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st);
 int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st);
 

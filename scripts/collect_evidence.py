@@ -93,3 +93,40 @@ json.dump({"128x28^2/fused_bwd@1024": {"traffic_bytes_per_launch": sum(traffic) 
                                                   "--cache-control none)" % tag}},
           open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, "%s_ncu_dominant_l2_bwd_128x28_n1024.txt" % tag)).read()[-900:])
+
+# tcgen05 FC GEMM
+rep = os.path.join(G, "umma_gemm_prof.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    hdr, units = rr[0], rr[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    want = ["Kernel Name", "Grid Size", "Block Size", "launch__cluster_size", "gpu__time_duration.sum",
+            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+    sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "greedy_multimodal_learning_b200", "csrc", "build",
+                                                              "gemm_kernels.o")], capture_output=True, text=True).stdout
+    counts = collections.Counter()
+    for line in sass.splitlines():
+        for m in ("UTCHMMA", "UTCBAR", "LDTM", "UTCATOMSWS", "LDGSTS", "HMMA.1688.F32.TF32", "SYNCS", "UCGABAR"):
+            if m in line:
+                counts[m] += 1
+    with open(os.path.join(P, "%s_ncu_umma_fc_gemm.txt" % tag), "w") as f:
+        f.write("ncu --set full --clock-control none --cache-control none --import-source on -k regex:gemm_umma -c 2 : "
+                "python scripts/gemm_accuracy.py\ntcgen05 3xTF32 FC GEMM (gemm_umma_kernel), C[1024,512] = A[1024,1024] "
+                "B[512,1024]^T, 32 tiles x 4-way split-K as 4-CTA clusters\n")
+        for x in rr[2:]:
+            f.write("----\n")
+            for w in want:
+                if w in idx:
+                    f.write("  %-62s %s %s\n" % (w, x[idx[w]][:90], units[idx[w]]))
+        f.write("\nSASS mnemonics in gemm_kernels.o (cuobjdump -sass): " +
+                ", ".join("%s x%d" % kv for kv in sorted(counts.items())) + "\n")
+        acc = os.path.join(G, "gemm_accuracy.log")
+        if os.path.exists(acc):
+            f.write("\nscripts/gemm_accuracy.py on the same box (max abs error vs float64 on N(0,1) operands; time per "
+                    "gml_fc_gemm call incl. ~11 us of launch floor; effective fp32 TFLOP/s):\n" + open(acc).read())
+    print(open(os.path.join(P, "%s_ncu_umma_fc_gemm.txt" % tag)).read())

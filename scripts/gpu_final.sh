@@ -16,3 +16,8 @@ CMD2="python scripts/sweep.py --batches 1024 --iters 1 --variants auto --out gpu
 timeout 300 $CMD2 > gpurun_out/ncu_plain2.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --cache-control none --import-source on -k regex:l2_bwd -c 2 -f -o gpurun_out/dominant_prof $CMD2 > gpurun_out/ncu_full2.log 2>&1
 echo "ncu full exit $?"
+echo "== ncu full (tcgen05 FC GEMM)"
+CMD3="python scripts/gemm_accuracy.py"
+timeout 300 $CMD3 > gpurun_out/gemm_accuracy.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --cache-control none --import-source on -k regex:gemm_umma -c 2 -f -o gpurun_out/umma_gemm_prof $CMD3 > gpurun_out/ncu_full3.log 2>&1
+echo "ncu umma exit $?"
