@@ -148,8 +148,11 @@ struct ColsumBatch {
   int block_start[5];
 };
 
-__global__ void __launch_bounds__(256) colsum_kernel(const ColsumBatch b) {
-  __shared__ float part[8][33];
+// 32 columns x 32 row groups per block: a warp reads 128 contiguous bytes of one row, every thread keeps up to 16
+// loads in flight (the kernel is pure L2/HBM latency: a [1024, 512] input is 2 MB).  Fixed summation order.
+constexpr int COLSUM_THREADS = 1024;
+__global__ void __launch_bounds__(COLSUM_THREADS) colsum_kernel(const ColsumBatch b) {
+  __shared__ float part[32][33];
   int sid = 0;
 #pragma unroll
   for (int i = 1; i < 4; ++i)
@@ -157,23 +160,32 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColsumBatch b) {
   const ColsumSeg s = sid == 0 ? b.seg[0] : (sid == 1 ? b.seg[1] : (sid == 2 ? b.seg[2] : b.seg[3]));
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = (blockIdx.x - b.block_start[sid]) * 32 + tx;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float acc = 0.f;
   if (j < s.cols) {
+    const float* col = s.x + j;
     int i = ty;
-    for (; i + 24 < s.rows; i += 32) {  // 4 independent loads in flight
-      a0 += s.x[(size_t)i * s.ld + j];
-      a1 += s.x[(size_t)(i + 8) * s.ld + j];
-      a2 += s.x[(size_t)(i + 16) * s.ld + j];
-      a3 += s.x[(size_t)(i + 24) * s.ld + j];
+    for (; i + 15 * 32 < s.rows; i += 16 * 32) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = col[(size_t)(i + 32 * u) * s.ld];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) acc += v[u];
     }
-    for (; i < s.rows; i += 8) a0 += s.x[(size_t)i * s.ld + j];
+    for (; i + 3 * 32 < s.rows; i += 4 * 32) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = col[(size_t)(i + 32 * u) * s.ld];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += v[u];
+    }
+    for (; i < s.rows; i += 32) acc += col[(size_t)i * s.ld];
   }
-  part[ty][tx] = (a0 + a1) + (a2 + a3);
+  part[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && j < s.cols) {
     float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += part[r][tx];
+    for (int r = 0; r < 32; ++r) t += part[r][tx];
     s.out[j] = t;
     if (s.run_v) {
       const float mean = t / s.n_total;
@@ -253,7 +265,7 @@ int launch_colsums(const ColsumSeg* segs, int count, cudaStream_t st) {
   b.block_start[4] = blocks;
   for (int i = count; i < 4; ++i) b.block_start[i] = blocks;  // unreachable segments
   { LaunchScope ls(kTagSmall, st);
-  colsum_kernel<<<blocks, 256, 0, st>>>(b); }
+  colsum_kernel<<<blocks, COLSUM_THREADS, 0, st>>>(b); }
   GML_LAUNCH_CHECK();
   return GML_OK;
 }
