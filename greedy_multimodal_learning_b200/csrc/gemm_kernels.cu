@@ -1083,13 +1083,10 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
 #define GML_GEMM(AK, BKC)                                                                                   \
   do {                                                                                                      \
     if (umma) {                                                                                             \
-      static bool attr_set = false;                                                                         \
-      const size_t sm = (size_t)USTAGES * U_STAGE_BYTES + 1024;                                                   \
-      if (!attr_set) {                                                                                      \
-        GML_CUDA_TRY(cudaFuncSetAttribute(gemm_umma_kernel<AK, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)sm));                                                        \
-        attr_set = true;                                                                                    \
-      }                                                                                                     \
+      const size_t sm = (size_t)USTAGES * U_STAGE_BYTES + 1024;                                              \
+      /* per device and cheap: set on every launch (a process may drive several GPUs) */                    \
+      GML_CUDA_TRY(cudaFuncSetAttribute(gemm_umma_kernel<AK, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                        (int)sm));                                                          \
       cudaLaunchConfig_t cfg = {};                                                                          \
       cfg.gridDim = grid; cfg.blockDim = dim3(UTHREADS); cfg.dynamicSmemBytes = sm; cfg.stream = st;         \
       cudaLaunchAttribute attr[1];                                                                          \
