@@ -425,6 +425,7 @@ def bench_train(torch, pkg, gdist, dev, world, rank, args, sync_ranks, max_over_
     """training_guided.gin step: batch `--train-batch` per GPU, data parallel when world > 1."""
     bsz = args.train_batch
     gdist.seed_everything(777)
+    torch.backends.cudnn.benchmark = True  # let cuDNN pick its convolution algorithms during the warm-up steps
     model = pkg.MMTM_MVCNN().to(dev)
     if world > 1:
         model, opt, reducer = gdist.setup_model(model, lambda p: torch.optim.SGD(p, lr=0.1, momentum=0, weight_decay=0))
@@ -464,7 +465,7 @@ def bench_train(torch, pkg, gdist, dev, world, rank, args, sync_ranks, max_over_
     roofline_sps = peak * 1e9 / 7_024_640 * world
     return {"samples_per_s": sps, "ms_per_step": ms, "global_batch": bsz * world, "steps": steps,
             "config": "training_guided.gin: 2-view ResNet-18 + MMTM, 224x224, SGD lr 0.1, Bias_Mitigation_Strong "
-                      "eps 0.01 window 5, fp32 (cuDNN TF32 default on), per-step H2D of the batch (prefetched one step ahead) "
+                      "eps 0.01 window 5, fp32 (cuDNN TF32 default on, cudnn.benchmark), per-step H2D of the batch (prefetched one step ahead) "
                       "and loss/acc read-back timed",
             "frac_of_mmtm_memory_roofline": sps / roofline_sps,
             "curation_mode_at_end": bool(engine.curation_mode)}

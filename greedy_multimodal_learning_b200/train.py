@@ -16,6 +16,7 @@ from .utils import gin_wrap
 @gin_lite.configurable
 def train(save_path, wd, lr, momentum, batch_size, callbacks=[]):
     multi = dist.init_from_env()  # torchrun environment -> one process per GPU
+    torch.backends.cudnn.benchmark = True  # fixed input shapes: let cuDNN time its convolution algorithms once
     dev = torch.device("cuda:%d" % torch.cuda.current_device()) if torch.cuda.is_available() else None
     model = MMTM_MVCNN()
     train_loader, valid, test = dataset.get_mvdcndata(batch_size=batch_size)

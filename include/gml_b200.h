@@ -87,8 +87,16 @@ void gml_profile_reset(void);
 int gml_profile_read(int tag, double* total_ms, int64_t* launches);
 /* Process-wide tuning knobs for measurement sweeps (defaults are what ships):
  *   "l2_chunk_mb"    bytes of feature map the streaming path pushes through both passes at once
- *   "fused_cluster"  0 auto | 4 (one CTA per SM) | 8 (two CTAs per SM)
- *   "fused_threads"  0 auto | 256 | 512                                                      */
+ *   "fused_kind"     0 auto | 1 shared-memory-resident cluster kernels | 2 L2-resident cluster kernels
+ *   "fused_cluster"  0 auto | 4 | 8 | 16 CTAs per cluster
+ *   "fused_threads"  0 auto | 256 | 512
+ *   "fused_occ", "fused_stash_kb", "fused_group_kb", "fused_prefetch", "fused_weight_ratio_x100"
+ *                    occupancy / stash / group size / L2 prefetch distance / path-selection threshold
+ *   "gemm_umma"      1 tcgen05 (TMEM) 3xTF32 kernel for FC problems above ~1e8 MACs | 0 never
+ *   "gemm_tf32x3"    1 mma.sync 3xTF32 for large problems the tcgen05 kernel does not take | 0 CUDA cores
+ *   "gemm_big_tiles" 1 opt-in 128x128 CUDA-core tiles
+ *   "overlap_wgrad"  1 weight-gradient GEMMs on the library's side stream (streaming backward)
+ *   "fused_trace_ptr", "gemm_trace_ptr"  device buffers for per-phase timing stamps (debug)        */
 int gml_set_tunable(const char* name, int64_t value);
 
 /* ---------------------------------------------------------------------------------------
