@@ -246,7 +246,6 @@ extern int g_fused_occ;
 extern int g_gemm_big_tiles;
 extern int g_gemm_tf32x3;
 extern int g_gemm_umma;
-extern int g_gemm_umma_dbg;
 extern long long* g_gemm_trace;
 extern int g_fused_weight_ratio_x100;
 extern int g_fused_group_kb;
@@ -270,7 +269,6 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "gemm_big_tiles")) { g_gemm_big_tiles = value ? 1 : 0; return GML_OK; }
   if (!strcmp(name, "gemm_tf32x3")) { g_gemm_tf32x3 = value ? 1 : 0; return GML_OK; }
   if (!strcmp(name, "gemm_umma")) { g_gemm_umma = value ? 1 : 0; return GML_OK; }
-  if (!strcmp(name, "gemm_umma_dbg")) { g_gemm_umma_dbg = (int)value; return GML_OK; }
   if (!strcmp(name, "gemm_trace_ptr")) { g_gemm_trace = reinterpret_cast<long long*>(value); return GML_OK; }
   if (!strcmp(name, "fused_occ")) {
     if (value != 4 && value != 5) return GML_E_BADARG;

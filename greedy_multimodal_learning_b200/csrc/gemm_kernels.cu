@@ -24,7 +24,6 @@ namespace gml {
 int g_gemm_big_tiles = 0;  // tunable "gemm_big_tiles"
 int g_gemm_tf32x3 = 1;     // tunable "gemm_tf32x3": tensor-core 3xTF32 inner product (0 = CUDA-core FFMA)
 int g_gemm_umma = 1;       // tunable "gemm_umma": tcgen05 128x128 kernel for the large problems (0 = never)
-int g_gemm_umma_dbg = 0;   // experiment knob
 long long* g_gemm_trace = nullptr;  // debug: globaltimer stamps of CTA (0,0,0) of the tcgen05 kernel (device buffer, 64 slots)
 
 namespace {
@@ -44,8 +43,7 @@ struct PipeBatch {
   unsigned int* tickets; // [count][tiles_m * tiles_n]
   int splits;
   int k_per_split;       // multiple of BK
-  int dbg;
-  long long* trace;
+  long long* trace;      // debug: phase stamps of CTA (0,0,0) of the tcgen05 kernel, or nullptr
 };
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int src_bytes) {
@@ -1061,7 +1059,6 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
     --splits;
   }
   pb.splits = splits;
-  pb.dbg = g_gemm_umma_dbg;
   pb.trace = g_gemm_trace;
   pb.k_per_split = ceil_div(nk, splits) * bk;
   pb.tickets = nullptr;
