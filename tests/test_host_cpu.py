@@ -191,3 +191,29 @@ def test_state_dict_keys_match_reference_checkpoint_layout():
             assert "%s.%s.weight" % (blk, fc) in keys and "%s.%s.bias" % (blk, fc) in keys
     assert not any("running_avg" in k for k in keys)
     assert sum(p.numel() for p in m.parameters()) == 23_773_008
+
+
+def test_3xtf32_split_keeps_fp32_accuracy():
+    """Arithmetic model of the tensor-core FC GEMMs (gemm_kernels.cu): big = x with the low 13 mantissa bits
+    cleared (a TF32 number), small = x - big (exact in fp32; the TF32 datapath keeps its top 19 bits), and
+    small_a*big_b + big_a*small_b + big_a*big_b accumulated.  The dropped terms are ~2^-21 relative per
+    product -- fp32-SGEMM class -- whereas plain TF32 (big*big only) is ~2^-11."""
+    rs = np.random.RandomState(0)
+    a = rs.standard_normal((64, 1024)).astype(np.float32)
+    b = rs.standard_normal((48, 1024)).astype(np.float32)
+
+    def trunc_tf32(x):
+        return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    a_big, b_big = trunc_tf32(a), trunc_tf32(b)
+    a_small, b_small = a - a_big, b - b_big
+    assert np.array_equal(a_big.astype(np.float64) + a_small.astype(np.float64), a.astype(np.float64))  # exact split
+    a_small_t, b_small_t = trunc_tf32(a_small), trunc_tf32(b_small)
+    f = lambda x: x.astype(np.float64)
+    exact = f(a) @ f(b).T
+    three = f(a_small_t) @ f(b_big).T + f(a_big) @ f(b_small_t).T + f(a_big) @ f(b_big).T
+    one = f(a_big) @ f(b_big).T
+    scale = np.abs(exact).max()
+    err3, err1 = np.abs(three - exact).max() / scale, np.abs(one - exact).max() / scale
+    assert err3 < 1e-6, err3          # ~3e-7 here: at the fp32 accumulation noise of a length-1024 dot product
+    assert err1 > 100 * err3, (err1, err3)
