@@ -494,9 +494,22 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
         GemmDesc both[2] = {ga, gb};
         GML_TRY(launch_gemm(both, 2, st, gws, gws_bytes));
       } else if (la && lb) {
-        GML_TRY(launch_gemm(&ga, 1, st, gws, gws_bytes));
-        gb.beta = 1;
-        GML_TRY(launch_gemm(&gb, 1, st, gws, gws_bytes));
+        // dH = ([dE_a | dE_b] [W_v ; W_s]) * [H > 0]: one launch over the concatenated K when the pipelined
+        // kernels can take it, else two accumulating launches
+        GemmDesc gm = ga;
+        gm.k = d.c_v + d.c_s;
+        gm.k_split = d.c_v;
+        gm.a2 = gb.a; gm.b2 = gb.b; gm.lda2 = gb.lda; gm.ldb2 = gb.ldb;
+        gm.act = kActReluMask;
+        int rc = GML_E_UNSUPPORTED;
+        if (gemm_ksplit_ok(gm) && gws) rc = launch_gemm(&gm, 1, st, gws, gws_bytes);
+        if (rc == GML_E_UNSUPPORTED) {
+          GML_TRY(launch_gemm(&ga, 1, st, gws, gws_bytes));
+          gb.beta = 1;
+          GML_TRY(launch_gemm(&gb, 1, st, gws, gws_bytes));
+        } else {
+          GML_TRY(rc);
+        }
       } else if (la) {
         ga.act = kActReluMask;
         GML_TRY(launch_gemm(&ga, 1, st, gws, gws_bytes));

@@ -226,6 +226,8 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st, void* ws, siz
     const int rc = launch_gemm_pipelined(descs, count, ws, ws_bytes, st);
     if (rc != GML_E_UNSUPPORTED) return rc;
   }
+  for (int i = 0; i < count; ++i)
+    if (descs[i].k_split) return GML_E_UNSUPPORTED;  // the generic kernel knows one K segment only
   GemmBatch batch;
   int max_m = 0, max_n = 0;
   for (int i = 0; i < count; ++i) {

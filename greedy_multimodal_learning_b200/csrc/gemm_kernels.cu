@@ -105,6 +105,13 @@ __device__ __forceinline__ void frag(const float* s, int t_idx, int kk, float (&
   }
 }
 
+// operand pointers / bounds for the k-tile starting at absolute k0 (second K segment: see GemmDesc)
+struct KSeg { const float* a; const float* b; int lda, ldb, k0, kmax; };
+__device__ __forceinline__ KSeg k_segment(const GemmDesc& d, int k0, int k_end) {
+  if (d.k_split && k0 >= d.k_split) return KSeg{d.a2, d.b2, d.lda2, d.ldb2, k0 - d.k_split, k_end - d.k_split};
+  return KSeg{d.a, d.b, d.lda, d.ldb, k0, d.k_split ? min(k_end, d.k_split) : k_end};
+}
+
 __device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ float epilogue(const GemmDesc& d, float v, int m, int n, const float* cp) {
@@ -142,8 +149,9 @@ __global__ void __launch_bounds__(THREADS, TM == 4 ? 3 : 1) gemm_pipe_kernel(con
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_tile<A_KC, BM>(As[s], d.a, d.lda, m0, d.m, k_begin + s * BK, k_end, tid);
-      load_tile<B_KC, BN>(Bs[s], d.b, d.ldb, n0, d.n, k_begin + s * BK, k_end, tid);
+      const KSeg ks = k_segment(d, k_begin + s * BK, k_end);
+      load_tile<A_KC, BM>(As[s], ks.a, ks.lda, m0, d.m, ks.k0, ks.kmax, tid);
+      load_tile<B_KC, BN>(Bs[s], ks.b, ks.ldb, n0, d.n, ks.k0, ks.kmax, tid);
     }
     cp_async_commit();
   }
@@ -152,8 +160,9 @@ __global__ void __launch_bounds__(THREADS, TM == 4 ? 3 : 1) gemm_pipe_kernel(con
     __syncthreads();
     const int nxt = kt + STAGES - 1;
     if (nxt < nk) {
-      load_tile<A_KC, BM>(As[nxt % STAGES], d.a, d.lda, m0, d.m, k_begin + nxt * BK, k_end, tid);
-      load_tile<B_KC, BN>(Bs[nxt % STAGES], d.b, d.ldb, n0, d.n, k_begin + nxt * BK, k_end, tid);
+      const KSeg ks = k_segment(d, k_begin + nxt * BK, k_end);
+      load_tile<A_KC, BM>(As[nxt % STAGES], ks.a, ks.lda, m0, d.m, ks.k0, ks.kmax, tid);
+      load_tile<B_KC, BN>(Bs[nxt % STAGES], ks.b, ks.ldb, n0, d.n, ks.k0, ks.kmax, tid);
     }
     cp_async_commit();
     const float* as = As[kt % STAGES];
@@ -313,8 +322,9 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_mma_kernel(const PipeBatch pb
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_tile<A_KC, BM, MPITCH_MN>(As[s], d.a, d.lda, m0, d.m, k_begin + s * BK, k_end, tid);
-      load_tile<B_KC, BN, MPITCH_MN>(Bs[s], d.b, d.ldb, n0, d.n, k_begin + s * BK, k_end, tid);
+      const KSeg ks = k_segment(d, k_begin + s * BK, k_end);
+      load_tile<A_KC, BM, MPITCH_MN>(As[s], ks.a, ks.lda, m0, d.m, ks.k0, ks.kmax, tid);
+      load_tile<B_KC, BN, MPITCH_MN>(Bs[s], ks.b, ks.ldb, n0, d.n, ks.k0, ks.kmax, tid);
     }
     cp_async_commit();
   }
@@ -323,8 +333,9 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_mma_kernel(const PipeBatch pb
     __syncthreads();
     const int nxt = kt + STAGES - 1;
     if (nxt < nk) {
-      load_tile<A_KC, BM, MPITCH_MN>(As[nxt % STAGES], d.a, d.lda, m0, d.m, k_begin + nxt * BK, k_end, tid);
-      load_tile<B_KC, BN, MPITCH_MN>(Bs[nxt % STAGES], d.b, d.ldb, n0, d.n, k_begin + nxt * BK, k_end, tid);
+      const KSeg ks = k_segment(d, k_begin + nxt * BK, k_end);
+      load_tile<A_KC, BM, MPITCH_MN>(As[nxt % STAGES], ks.a, ks.lda, m0, d.m, ks.k0, ks.kmax, tid);
+      load_tile<B_KC, BN, MPITCH_MN>(Bs[nxt % STAGES], ks.b, ks.ldb, n0, d.n, ks.k0, ks.kmax, tid);
     }
     cp_async_commit();
     const float* as = As[kt % STAGES];
@@ -695,9 +706,9 @@ __global__ void __launch_bounds__(UTHREADS, 1) gemm_umma_kernel(const PipeBatch 
     };
     auto issue_loads = [&](int kt) {
       unsigned char* st = u_smem + (kt % USTAGES) * U_STAGE_BYTES;
-      const int k0 = k_begin + kt * UK;
-      u_load_tile<A_KC>(st, d.a, d.lda, m0, d.m, k0, k_end, warp, lane);
-      u_load_tile<B_KC>(st + 2 * U_TILE_BYTES, d.b, d.ldb, n0, d.n, k0, k_end, warp, lane);
+      const KSeg ks = k_segment(d, k_begin + kt * UK, k_end);
+      u_load_tile<A_KC>(st, ks.a, ks.lda, m0, d.m, ks.k0, ks.kmax, warp, lane);
+      u_load_tile<B_KC>(st + 2 * U_TILE_BYTES, ks.b, ks.ldb, n0, d.n, ks.k0, ks.kmax, warp, lane);
     };
 #pragma unroll
     for (int s = 0; s < USTAGES - 1; ++s) {
@@ -990,10 +1001,16 @@ bool pipe_ok(const GemmDesc& d) {
   // operands) K multiples of 4
   if (!aligned16(d.a) || !aligned16(d.b) || d.lda % 4 || d.ldb % 4) return false;
   if ((d.a_kc || d.b_kc) && d.k % 4) return false;
+  if (d.k_split) {  // a k-tile (16 or 32 wide) must never straddle the two segments
+    if (d.k_split % 32 || d.k_split >= d.k || !d.a2 || !d.b2) return false;
+    if (!aligned16(d.a2) || !aligned16(d.b2) || d.lda2 % 4 || d.ldb2 % 4) return false;
+  }
   return true;
 }
 
 }  // namespace
+
+bool gemm_ksplit_ok(const GemmDesc& d) { return pipe_ok(d); }
 
 // Zero the ticket block once per C-ABI call; every split-K launch leaves it zeroed again.
 int prepare_gemm_workspace(void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -1026,7 +1043,9 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   if (count == 2 && descs[0].k != descs[1].k) return GML_E_UNSUPPORTED;
   // 128x128 tiles (gemm_big_kernel, 8x8 outputs per thread) measured SLOWER than the 64x64 cp.async kernel at
   // 3 CTAs per SM on every FC shape of the three blocks (profiles/r1_experiments.md), so they are opt-in only.
-  const bool big = g_gemm_big_tiles && (long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * count >= 24 && min_k >= 64;
+  bool any_ksplit = false;
+  for (int i = 0; i < count; ++i) any_ksplit |= descs[i].k_split != 0;
+  const bool big = g_gemm_big_tiles && !any_ksplit && (long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * count >= 24 && min_k >= 64;
   // tcgen05 kernel: worth its fixed costs (TMEM allocation, 192 KB of shared memory, one CTA per SM) only for the
   // big FC problems (batch >= ~512 on the 256- and 512-channel blocks)
   // tensor cores only pay off on the large problems (measured cross-over, scripts/gemm_accuracy.py); everything

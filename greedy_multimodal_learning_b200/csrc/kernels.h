@@ -61,7 +61,13 @@ struct GemmDesc {
   int a_kc, b_kc;
   int act;
   int beta;           // 0 or 1
+  // optional second K segment: for k >= k_split the operands come from a2 / b2 (addressed with k - k_split and
+  // lda2 / ldb2), i.e. C = [A | A2] [B | B2]^T in one launch.  k_split == 0: none.  Only the pipelined kernels
+  // support it (gemm_ksplit_ok); k_split must be a multiple of 32.
+  const float* a2; const float* b2;
+  int lda2, ldb2, k_split;
 };
+bool gemm_ksplit_ok(const GemmDesc& d);
 // up to two independent problems in one launch (blockIdx.z).  With a workspace of
 // gemm_workspace_bytes() the pipelined split-K kernel (gemm_kernels.cu) is used whenever the operands
 // are 16-byte aligned; otherwise the generic register-staged kernel (fc_kernels.cu).
