@@ -431,7 +431,7 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   // weight gradients over the whole batch (reduction over samples inside one CTA per tile or split-K
   // with an ordered fold: deterministic, no atomics)
   auto weight_grads = [&](cudaStream_t ws_stream, void* ws_mem) -> int {
-    GemmDesc gw[2];
+    GemmDesc gw[3];
     int cw = 0;
     if (d_w_v) {
       if (la) gw[cw++] = GemmDesc{de_a, h, d_w_v, nullptr, nullptr, d.c_v, d.d, d.n, d.c_v, d.d, d.d, 0, 0, 0, kActNone, 0};
@@ -441,11 +441,16 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
       if (lb) gw[cw++] = GemmDesc{de_b, h + (size_t)d.hoff * d.d, d_w_s, nullptr, nullptr, d.c_s, d.d, d.n, d.c_s, d.d, d.d, 0, 0, 0, kActNone, 0};
       else GML_TRY(launch_fill_zero(d_w_s, (size_t)d.c_s * d.d, ws_stream));
     }
-    if (cw) GML_TRY(launch_gemm(gw, cw, ws_stream, ws_mem, gws_bytes));
     if (d_w_sq) {
+      // dW_sq reduces over the same samples as dW_v / dW_s unless the hidden state is doubled (mode 3): one launch
       GemmDesc gq{dh, z, d_w_sq, nullptr, nullptr, d.d, d.ldz, d.zrows, d.d, d.ldz, d.ldz, 0, 0, 0, kActNone, 0};
-      GML_TRY(launch_gemm(&gq, 1, ws_stream, ws_mem, gws_bytes));
+      if (cw && d.zrows == d.n) {
+        gw[cw++] = gq;
+      } else {
+        GML_TRY(launch_gemm(&gq, 1, ws_stream, ws_mem, gws_bytes));
+      }
     }
+    if (cw) GML_TRY(launch_gemm(gw, cw, ws_stream, ws_mem, gws_bytes));
     ColsumSeg segs[3];
     int nseg = 0;
     if (d_b_v) {

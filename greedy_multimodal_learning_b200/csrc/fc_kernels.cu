@@ -221,10 +221,14 @@ __global__ void fill_zero_kernel(float* p, size_t n) {
 }  // namespace
 
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t st, void* ws, size_t ws_bytes) {
-  if (count < 1 || count > 2) return GML_E_BADARG;
+  if (count < 1 || count > 3) return GML_E_BADARG;
   {
     const int rc = launch_gemm_pipelined(descs, count, ws, ws_bytes, st);
     if (rc != GML_E_UNSUPPORTED) return rc;
+  }
+  if (count == 3) {  // the generic kernel batches two problems
+    const int rc = launch_gemm(descs, 2, st, ws, ws_bytes);
+    return rc != GML_OK ? rc : launch_gemm(descs + 2, 1, st, ws, ws_bytes);
   }
   for (int i = 0; i < count; ++i)
     if (descs[i].k_split) return GML_E_UNSUPPORTED;  // the generic kernel knows one K segment only

@@ -38,8 +38,8 @@ template <int BT> struct TileGeom {
 };
 
 struct PipeBatch {
-  GemmDesc d[2];
-  float* part[2];        // split-K partials per problem: [splits][m][n]
+  GemmDesc d[3];         // up to three independent problems per launch (blockIdx.z / splits)
+  float* part[3];        // split-K partials per problem: [splits][m][n]
   unsigned int* tickets; // [count][tiles_m * tiles_n]
   int splits;
   int k_per_split;       // multiple of BK
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, TM == 4 ? 3 : 1) gemm_pipe_kernel(con
   float (*Bs)[TILE_FLOATS] = reinterpret_cast<float (*)[TILE_FLOATS]>(gemm_smem + STAGES * TILE_FLOATS);
   __shared__ unsigned int s_ticket;
   const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
-  const GemmDesc d = prob ? pb.d[1] : pb.d[0];
+  const GemmDesc d = prob == 0 ? pb.d[0] : (prob == 1 ? pb.d[1] : pb.d[2]);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (m0 >= d.m || n0 >= d.n) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_mma_kernel(const PipeBatch pb
   float (*Bs)[MMA_TILE_FLOATS] = reinterpret_cast<float (*)[MMA_TILE_FLOATS]>(gemm_smem + STAGES * MMA_TILE_FLOATS);
   __shared__ unsigned int s_ticket;
   const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
-  const GemmDesc d = prob ? pb.d[1] : pb.d[0];
+  const GemmDesc d = prob == 0 ? pb.d[0] : (prob == 1 ? pb.d[1] : pb.d[2]);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (m0 >= d.m || n0 >= d.n) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) gemm_umma_kernel(const PipeBatch 
   __shared__ __align__(8) uint64_t bar_full[USTAGES], bar_empty[USTAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t s_tmem;
     const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
-  const GemmDesc d = prob ? pb.d[1] : pb.d[0];
+  const GemmDesc d = prob == 0 ? pb.d[0] : (prob == 1 ? pb.d[1] : pb.d[2]);
   const int m0 = blockIdx.y * UM, n0 = blockIdx.x * UN;
   if (m0 >= d.m || n0 >= d.n) return;  // uniform for the CTA, before anything is allocated
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_big_kernel(const PipeBatch pb
   __shared__ __align__(16) float Bs[2][GK][GPITCH];
   __shared__ unsigned int s_ticket;
   const int prob = blockIdx.z / pb.splits, split = blockIdx.z - prob * pb.splits;
-  const GemmDesc d = prob ? pb.d[1] : pb.d[0];
+  const GemmDesc d = prob == 0 ? pb.d[0] : (prob == 1 ? pb.d[1] : pb.d[2]);
   const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
   if (m0 >= d.m || n0 >= d.n) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -1027,7 +1027,7 @@ size_t gemm_workspace_bytes() {
 
 // returns GML_E_UNSUPPORTED when the problems do not meet the pipeline's alignment rules
 int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (count < 1 || count > 2) return GML_E_BADARG;
+  if (count < 1 || count > 3) return GML_E_BADARG;
   PipeBatch pb;
   int max_m = 0, max_n = 0, min_k = 1 << 30;
   for (int i = 0; i < count; ++i) {
@@ -1039,8 +1039,9 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
     max_n = descs[i].n > max_n ? descs[i].n : max_n;
     min_k = descs[i].k < min_k ? descs[i].k : min_k;
   }
-  if (count == 1) pb.d[1] = descs[0];
-  if (count == 2 && descs[0].k != descs[1].k) return GML_E_UNSUPPORTED;
+  for (int i = count; i < 3; ++i) pb.d[i] = descs[0];
+  for (int i = 1; i < count; ++i)
+    if (descs[i].k != descs[0].k) return GML_E_UNSUPPORTED;
   // 128x128 tiles (gemm_big_kernel, 8x8 outputs per thread) measured SLOWER than the 64x64 cp.async kernel at
   // 3 CTAs per SM on every FC shape of the three blocks (profiles/r1_experiments.md), so they are opt-in only.
   bool any_ksplit = false;
@@ -1056,10 +1057,12 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   const int BM = (big || umma) ? 128 : 64, BN = BM;
   const int bk = umma ? UK : BK;
   const int tiles_m = ceil_div(max_m, BM), tiles_n = ceil_div(max_n, BN);
-  const long tiles = (long)tiles_m * tiles_n * count;
+  const long tiles = (long)tiles_m * tiles_n * count;  // grid extent (CTAs outside their problem exit at once)
+  long busy = 0;                                        // tiles that actually compute
+  for (int i = 0; i < count; ++i) busy += (long)ceil_div(descs[i].m, BM) * ceil_div(descs[i].n, BN);
   const int nk = ceil_div(min_k, bk);
-  // tcgen05 kernel: one CTA per SM (shared memory), so the grid must fit ONE wave: splits = floor(SMs / tiles)
-  int splits = umma ? (int)(kNumSMs / tiles) : (int)((2 * kNumSMs + tiles - 1) / tiles);
+  // tcgen05 kernel: one CTA per SM (shared memory), so the busy CTAs must fit ONE wave: splits = floor(SMs / busy)
+  int splits = umma ? (int)(kNumSMs / busy) : (int)((2 * kNumSMs + busy - 1) / busy);
   const int min_tiles_per_split = umma ? 2 : 4;
   if (splits > nk / min_tiles_per_split) splits = nk / min_tiles_per_split;
   if (splits > 16) splits = 16;
@@ -1081,7 +1084,7 @@ int launch_gemm_pipelined(const GemmDesc* descs, int count, void* ws, size_t ws_
   pb.trace = g_gemm_trace;
   pb.k_per_split = ceil_div(nk, splits) * bk;
   pb.tickets = nullptr;
-  pb.part[0] = pb.part[1] = nullptr;
+  pb.part[0] = pb.part[1] = pb.part[2] = nullptr;
   if (splits > 1 && !umma) {
     char* p = static_cast<char*>(ws);
     pb.tickets = reinterpret_cast<unsigned int*>(p);

@@ -68,7 +68,7 @@ struct GemmDesc {
   int lda2, ldb2, k_split;
 };
 bool gemm_ksplit_ok(const GemmDesc& d);
-// up to two independent problems in one launch (blockIdx.z).  With a workspace of
+// up to three independent problems in one launch (blockIdx.z; equal K and operand layouts).  With a workspace of
 // gemm_workspace_bytes() the pipelined split-K kernel (gemm_kernels.cu) is used whenever the operands
 // are 16-byte aligned; otherwise the generic register-staged kernel (fc_kernels.cu).
 size_t gemm_workspace_bytes();

@@ -267,7 +267,7 @@ def test_guided_training_trace_on_gpu():
         # batch-4 BatchNorm amplifies fp32 rounding differences from step to step even at this lr: tight
         # for the first steps, bounded drift afterwards (decisions and accuracy counts stay exact)
         assert abs(a["loss"] - b["loss"]) <= (1e-3 if i < 3 else 2e-2) * abs(b["loss"]), (i, a["loss"], b["loss"])
-        assert abs(a["d_BDR"] - b["d_BDR"]) <= (2e-3 if i < 4 else 1e-2), (i, a["d_BDR"], b["d_BDR"])
+        assert abs(a["d_BDR"] - b["d_BDR"]) <= (2e-3 if i < 3 else 1e-2), (i, a["d_BDR"], b["d_BDR"])
     for h, e in zip(hist_a, ref_hist):
         for k in ("val_acc", "test_acc", "val_acc_modal_0", "test_acc_modal_1"):
             assert h[k] == e[k], k
