@@ -217,3 +217,28 @@ def test_3xtf32_split_keeps_fp32_accuracy():
     err3, err1 = np.abs(three - exact).max() / scale, np.abs(one - exact).max() / scale
     assert err3 < 1e-6, err3          # ~3e-7 here: at the fp32 accumulation noise of a length-1024 dot product
     assert err1 > 100 * err3, (err1, err3)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch / CUDA types) and a C
+    program must link against the shared library and call it (no GPU needed for these two entry points)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    header_dir = os.path.join(ROOT, "include")
+    src = tmp_path / "main.c"
+    src.write_text('#include <stdio.h>\n#include "gml_b200.h"\n'
+                   "int main(void) {\n"
+                   "  gml_mmtm_dims d = {4, 8, 8, 16, 16, 4};\n"
+                   '  printf("%d %s %d %d\\n", gml_abi_version(), gml_error_string(GML_E_ALIGN), gml_kernel_tag_count(), '
+                   "(int)(gml_mmtm_bwd_workspace_bytes(&d) > 0));\n"
+                   "  return 0;\n}\n")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", header_dir, str(src)],
+                   check=True)
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "main"
+    subprocess.run(["gcc", "-std=c99", "-I", header_dir, str(src), "-o", str(exe), "-L", lib_dir, "-lgml_b200",
+                    "-Wl,-rpath," + lib_dir, "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == "1" and int(out[-2]) >= 10 and out[-1] == "1"
