@@ -1,0 +1,179 @@
+"""GPU parity at the BENCHMARKED configuration: the automatically selected kernel path at batch 256
+(`training_guided.gin`) and 1024 (top of BASELINE.json configs[1]) on the three real MMTM shapes, all four
+modes, EVERY output against the CPU oracle (`oracle.mmtm_oracle.forward_backward`, the restatement of
+reference src/balanced_mmtm.py:93-154) at the north_star tolerance of 1e-5; plus one guided training step
+of the full 2-view model at 224x224 (reference src/model.py:81-97, src/callbacks.py:199-233).
+
+Path selection depends on the batch (tile pipeline / cluster kernels / streaming), so the small-batch
+oracle tests in test_mmtm_gpu.py do not cover what bench.py times: these do.
+"""
+import numpy as np
+import pytest
+import torch
+
+import greedy_multimodal_learning_b200 as pkg
+from greedy_multimodal_learning_b200 import _lib
+from oracle import mmtm_oracle as mo
+from oracle import stats_oracle as so
+from oracle.mmtm_module import OracleMMTM
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+SHAPES = [(128, 28), (256, 14), (512, 7)]
+RTOL = 1e-5
+
+
+def _close_dev(x, ref, what, rtol=RTOL):
+    """tests/helpers.assert_close evaluated on the GPU in float64 (the tensors are up to 100 M elements)."""
+    x = x.to(DEV).double()
+    ref = ref.to(DEV).double()
+    assert x.shape == ref.shape, (what, x.shape, ref.shape)
+    scale = float(ref.abs().max())
+    err = (x - ref).abs()
+    worst = float(err.max())
+    assert worst <= rtol * max(scale, 1e-30), "%s: norm-relative error %.3e > %.0e" % (what, worst / max(scale, 1e-30), rtol)
+    bad = err > rtol * ref.abs() + 0.1 * rtol * scale
+    assert not bool(bad.any()), "%s: %d elements outside rtol=%g" % (what, int(bad.sum()), rtol)
+
+
+def _inputs(seed, n, c, h):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda: torch.randn(n, c, h, h, generator=g)
+    return dict(A=r(), B=r(), gA=r(), gB=r())
+
+
+def _ambiguous(x, p, mode, avg, rel=1e-5):
+    """tests/helpers.relu_ambiguous_samples in torch float64.  Same rule; the threshold is RELATIVE to the largest
+    pre-activation (1e-5 * max|pre|: the helper's 2e-5 at its max|H| ~ 2, proportionally tighter where the
+    pre-activations -- and their fp32 rounding noise -- are smaller, e.g. 1e-6 at 128x28^2)."""
+    a = x["A"].double().flatten(2).mean(2)
+    b = x["B"].double().flatten(2).mean(2)
+    w, bias = p.w_sq.double(), p.b_sq.double()
+    if mode == 3:
+        zs = [torch.cat([a, avg[1].double().expand(len(a), -1)], 1), torch.cat([avg[0].double().expand(len(b), -1), b], 1)]
+    else:
+        zs = [torch.cat([a, b], 1)]
+    amb = torch.zeros(len(a), dtype=torch.bool)
+    for z in zs:
+        pre = z @ w.T + bias
+        amb |= (pre.abs() < rel * float(pre.abs().max())).any(1)
+    return amb
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [256, 1024])
+@pytest.mark.parametrize("c,h", SHAPES, ids=["128x28", "256x14", "512x7"])
+def test_benchmarked_config_vs_oracle(c, h, n, mode):
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    x = _inputs(1000 * c + n + mode, n, c, h)
+    warm = _inputs(7, 3, c, h)
+    p = mo.synth_params(c + mode, c, c)
+    rs = np.random.RandomState(c)
+    avg = [torch.from_numpy((0.1 * rs.standard_normal(c)).astype(np.float32)) for _ in range(2)]
+    # hidden pre-activations inside fp32 rounding noise of zero make the ReLU mask undecidable (helpers.py):
+    # those samples get a zero upstream gradient; the bound on how many is part of the test
+    amb = _ambiguous(x, p, mode, avg)
+    assert int(amb.sum()) < 40, int(amb.sum())
+    x["gA"][amb] = 0
+    x["gB"][amb] = 0
+
+    m = pkg.MMTM_mitigate(c, c, 4)
+    with torch.no_grad():
+        for dst, src in zip((m.fc_squeeze.weight, m.fc_squeeze.bias, m.fc_visual.weight, m.fc_visual.bias,
+                             m.fc_skeleton.weight, m.fc_skeleton.bias), p.tensors()):
+            dst.copy_(src)
+    m = m.to(DEV)
+    with torch.no_grad():
+        m(warm["A"].to(DEV), warm["B"].to(DEV))      # step 1: the running means are no longer zero
+    a = x["A"].to(DEV).requires_grad_(True)
+    b = x["B"].to(DEV).requires_grad_(True)
+    kw = {}
+    if mode == 1:
+        kw = dict(curation_mode=True, caring_modality=0)
+    elif mode == 2:
+        kw = dict(curation_mode=True, caring_modality=1)
+    elif mode == 3:
+        kw = dict(turnoff_cross_modal_flow=True, average_squeezemaps=[t.to(DEV) for t in avg])
+    a_out, b_out, scales, sq = m(a, b, True, mode != 3, **kw)
+    torch.autograd.backward([a_out, b_out], [x["gA"].to(DEV), x["gB"].to(DEV)])
+    g = lambda q: torch.zeros_like(q) if q.grad is None else q.grad
+    got = dict(A_out=a_out.detach(), B_out=b_out.detach(), dA=a.grad, dB=b.grad, gA=scales[0], gB=scales[1],
+               dWsq=g(m.fc_squeeze.weight), dbsq=g(m.fc_squeeze.bias), dWv=g(m.fc_visual.weight),
+               dbv=g(m.fc_visual.bias), dWs=g(m.fc_skeleton.weight), dbs=g(m.fc_skeleton.bias))
+    if sq is not None:
+        got["sA"], got["sB"] = sq
+
+    st = mo.MMTMState.zeros(c)
+    with torch.no_grad():
+        mo.forward(warm["A"], warm["B"], p, st, 0)
+    want = mo.forward_backward(x["A"], x["B"], p, st, x["gA"], x["gB"], mode, avg)
+    for k, v in got.items():
+        _close_dev(v, want[k], "%dx%d^2 n%d m%d %s" % (c, h, n, mode, k))
+    _close_dev(m.running_avg_weight_visual, st.run_v, "run_v", 1e-6)
+    _close_dev(m.running_avg_weight_skeleton, st.run_s, "run_s", 1e-6)
+    assert m.step == st.step == 2
+    # a substituted side's excitation FC gets no gradient, like the reference's autograd
+    assert (m.fc_visual.weight.grad is not None) == want["has_grad"]["w_v"]
+    assert (m.fc_skeleton.weight.grad is not None) == want["has_grad"]["w_s"]
+
+
+def test_guided_step_224_vs_oracle_hot_path():
+    """north_star: 'identical synthetic 2-view 224x224 inputs and seeds'.  One guided training step of
+    MMTM_MVCNN at batch 8 (training_random.gin's batch): product hot path (CUDA MMTM fwd/bwd, one-launch
+    learning-speed statistic, device accuracy counts) vs the oracle hot path on the SAME cuDNN backbone,
+    so only the path under test differs."""
+    BR, MM = ["net_view_0", "net_view_1"], ["visual", "skeleton"]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    g = torch.Generator().manual_seed(224)
+    x = torch.randn(8, 2, 3, 224, 224, generator=g).to(DEV)
+    y = torch.randint(0, 40, (8,), generator=g).to(DEV)
+    try:
+        res = {}
+        for name, cls in (("cuda", pkg.MMTM_mitigate), ("oracle", OracleMMTM)):
+            torch.manual_seed(777)
+            model = pkg.MMTM_MVCNN(mmtm_cls=cls).to(DEV).train()
+            fused, views, _, _ = model(x)
+            loss = pkg.blend_loss(views, y)
+            loss.backward()
+            res[name] = dict(model=model, fused=fused.detach(), views=[v.detach() for v in views], loss=float(loss))
+    finally:
+        torch.backends.cudnn.deterministic = False
+    a, b = res["cuda"], res["oracle"]
+    assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(b["loss"]), (a["loss"], b["loss"])
+    _close_dev(a["fused"], b["fused"], "fused logits", 2e-5)
+    # predicted labels and accuracy counts: bit-exact (integers)
+    for va, vb in zip([a["fused"]] + a["views"], [b["fused"]] + b["views"]):
+        assert torch.equal(va.argmax(1), vb.argmax(1))
+    counts = torch.empty(3, dtype=torch.int32, device=DEV)
+    lib = _lib.load()
+    _lib.check(lib.gml_accuracy_counts(a["views"][0].contiguous().data_ptr(), a["views"][1].contiguous().data_ptr(),
+                                       y.data_ptr(), 8, 40, counts.data_ptr(), _lib.current_stream(torch.device(DEV))))
+    want = [so.correct_count(t.cpu(), y.cpu())[0] for t in [b["fused"]] + b["views"]]
+    assert counts.tolist() == want
+    # every parameter gradient of the whole model (the backward of the three blocks feeds all of them)
+    pa, pb = dict(a["model"].named_parameters()), dict(b["model"].named_parameters())
+    # (tolerance: the two runs differ by ~1e-7 relative at the MMTM outputs; batch-8 BatchNorm + ReLU chains of
+    # the backbone amplify that on the way back to the stem -- measured 5e-4 at conv1 -- so backbone gradients get
+    # 2e-3, the MMTM blocks' own parameter gradients 2e-4)
+    worst = {}
+    for k in pa:
+        tol = 2e-4 if k.startswith("mmtm") else 2e-3
+        sc = float(pb[k].grad.abs().max())
+        worst[k] = float((pa[k].grad - pb[k].grad).abs().max()) / max(sc, 1e-30)
+        assert worst[k] <= tol, "grad %s: norm-relative error %.3e > %.0e" % (k, worst[k], tol)
+    print("worst gradient error: %s %.2e" % max(worst.items(), key=lambda kv: kv[1]))
+    # learning-speed statistic: one launch over the product's 142 params + grads vs the reference's
+    # per-tensor loop (callbacks.py:203-223) on the same tensors, 1e-6 relative; then across the two runs
+    got = pkg.MultiTensorSqnorm(a["model"].named_parameters(), BR, MM).measure()
+    same = so.sqnorm_buckets(((n_, p_.detach().cpu(), p_.grad.cpu()) for n_, p_ in a["model"].named_parameters()), BR, MM)
+    other = so.sqnorm_buckets(((n_, p_.detach().cpu(), p_.grad.cpu()) for n_, p_ in b["model"].named_parameters()), BR, MM)
+    for k in same:
+        for i in (0, 1):
+            assert abs(got[k][i] - same[k][i]) <= 1e-6 * same[k][i], (k, i)
+            assert abs(got[k][i] - other[k][i]) <= 1e-4 * other[k][i], (k, i)
+    d_got = so.LearningSpeed().update(got)
+    d_ref = so.LearningSpeed().update(other)
+    assert abs(d_got - d_ref) <= 1e-4, (d_got, d_ref)
