@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libgml_b200.so")
 
 MODE_NORMAL, MODE_CURATE_VISUAL, MODE_CURATE_SKELETON, MODE_XMODAL_OFF = 0, 1, 2, 3
-F_NO_RUNNING_UPDATE, F_FORCE_STREAMING, F_FORCE_FUSED = 1, 2, 4
+F_NO_RUNNING_UPDATE, F_FORCE_STREAMING, F_FORCE_FUSED, F_FORCE_TILE = 1, 2, 4, 8
 BUCKET_MAIN0, BUCKET_MAIN1, BUCKET_BYPASS0, BUCKET_BYPASS1 = 1, 2, 4, 8
 
 

@@ -250,6 +250,7 @@ extern long long* g_gemm_trace;
 extern int g_fused_weight_ratio_x100;
 extern int g_fused_group_kb;
 extern int g_fused_stash_kb;
+extern int g_tile_kind, g_tile_lag, g_tile_gemm_ctas, g_tile_m, g_tile_chunk_kb, g_tile_min_mb;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -276,6 +277,15 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   }
   if (!strcmp(name, "fused_prefetch")) { g_fused_prefetch = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "fused_trace_ptr")) { g_fused_trace = reinterpret_cast<long long*>(value); return GML_OK; }
+  if (!strcmp(name, "tile_kind")) {
+    if (value < 0 || value > 2) return GML_E_BADARG;
+    g_tile_kind = (int)value; return GML_OK;
+  }
+  if (!strcmp(name, "tile_lag")) { g_tile_lag = value < 1 ? 1 : (value > 8 ? 8 : (int)value); return GML_OK; }
+  if (!strcmp(name, "tile_gemm_ctas")) { g_tile_gemm_ctas = value < 0 ? 0 : (int)value; return GML_OK; }
+  if (!strcmp(name, "tile_m")) { g_tile_m = value < 0 ? 0 : (value > 128 ? 128 : (int)value); return GML_OK; }
+  if (!strcmp(name, "tile_chunk_kb")) { g_tile_chunk_kb = value < 1 ? 1 : (value > 100 ? 100 : (int)value); return GML_OK; }
+  if (!strcmp(name, "tile_min_mb")) { g_tile_min_mb = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "fused_threads")) {
     if (value != 0 && value != 256 && value != 512) return GML_E_BADARG;
     g_fused_threads = (int)value; return GML_OK;
@@ -291,8 +301,12 @@ extern "C" int gml_device_is_blackwell(void) {
 }
 
 extern "C" size_t gml_mmtm_fwd_workspace_bytes(const gml_mmtm_dims* dims) {
-  (void)dims;
-  return gemm_workspace_bytes();  // split-K partials of the FC GEMMs (streaming path)
+  size_t need = gemm_workspace_bytes();  // split-K partials of the FC GEMMs (streaming path)
+  if (dims && dims->c_v == dims->c_s && dims->hw_v == dims->hw_s) {  // counters + split-K partials of the tile pipeline
+    const size_t t = tile_fwd_workspace_bytes(dims->n, dims->c_v, dims->hw_v, dims->d);
+    if (t > need) need = t;
+  }
+  return need;
 }
 
 extern "C" int gml_mmtm_gates(const float* a, const float* b, const float* w_sq, const float* b_sq, const float* w_v,
@@ -349,7 +363,19 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
   if (d.n == 0) return GML_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  const bool can_fuse = !(flags & GML_F_FORCE_STREAMING) && !curate &&
+  const bool can_tile = !(flags & (GML_F_FORCE_STREAMING | GML_F_FORCE_FUSED)) && !curate && workspace &&
+                        tile_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode) &&
+                        workspace_bytes >= tile_fwd_workspace_bytes(d.n, d.c_v, d.hw_v, d.d);
+  if ((flags & GML_F_FORCE_TILE) && !can_tile) return GML_E_UNSUPPORTED;
+  if (can_tile && ((flags & GML_F_FORCE_TILE) || tile_preferred(d.n, d.c_v, d.hw_v, d.d))) {
+    FusedFwdArgs fa{a, b, a_out, b_out, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, run_v, run_s,
+                    d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
+    const int rc = launch_tile_fwd(fa, gate_sum, update ? run_v : nullptr, update ? run_s : nullptr, (float)step,
+                                   workspace, workspace_bytes, st);
+    if (rc != GML_E_UNSUPPORTED || (flags & GML_F_FORCE_TILE)) return rc;  // unsupported = misaligned pointers
+  }
+
+  const bool can_fuse = !(flags & (GML_F_FORCE_STREAMING | GML_F_FORCE_TILE)) && !curate &&
                         fused_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
   if ((flags & GML_F_FORCE_FUSED) && !can_fuse) return GML_E_UNSUPPORTED;
   if (can_fuse && ((flags & GML_F_FORCE_FUSED) || fused_fwd_preferred(d.n, d.c_v, d.hw_v, d.d))) {
@@ -392,7 +418,10 @@ extern "C" size_t gml_mmtm_bwd_workspace_bytes(const gml_mmtm_dims* dims) {
   if (!dims || dims->n < 0) return 0;
   const size_t n = (size_t)dims->n, ldz = (size_t)dims->c_v + dims->c_s, dd = (size_t)dims->d;
   // de_a [N,c_v] + de_b [N,c_s] + dh [2N,D] + dz [2N,ldz]   (2N rows cover mode 3)
-  return 256 + sizeof(float) * (n * ldz + 2 * n * dd + 2 * n * ldz) + 4 * 256 + 2 * gemm_workspace_bytes();
+  size_t need = 256 + sizeof(float) * (n * ldz + 2 * n * dd + 2 * n * ldz) + 4 * 256 + 2 * round_up(gemm_workspace_bytes(), 256);
+  if (dims->c_v == dims->c_s && dims->hw_v == dims->hw_s)
+    need += tile_bwd_workspace_bytes(dims->n, dims->c_v, dims->hw_v, dims->d);
+  return need;
 }
 
 extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a, const float* b, const float* w_sq,
@@ -425,11 +454,13 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   void* gws = wp;
   const size_t gws_bytes = gemm_workspace_bytes();
   void* gws2 = wp + round_up(gws_bytes, 256);  // second split-K workspace for the side stream
+  void* tile_ws = wp + 2 * round_up(gws_bytes, 256);  // counters, partials, transposed weights of the tile pipeline
   GML_TRY(prepare_gemm_workspace(gws, gws_bytes, st));
   GML_TRY(prepare_gemm_workspace(gws2, gws_bytes, st));
 
   // weight gradients over the whole batch (reduction over samples inside one CTA per tile or split-K
   // with an ordered fold: deterministic, no atomics)
+  bool bias_done = false;  // the tile pipeline forms the bias gradients itself
   auto weight_grads = [&](cudaStream_t ws_stream, void* ws_mem) -> int {
     GemmDesc gw[3];
     int cw = 0;
@@ -451,6 +482,7 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
       }
     }
     if (cw) GML_TRY(launch_gemm(gw, cw, ws_stream, ws_mem, gws_bytes));
+    if (bias_done) return GML_OK;
     ColsumSeg segs[3];
     int nseg = 0;
     if (d_b_v) {
@@ -467,10 +499,25 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   };
   bool wgrad_done = false;
 
-  const bool can_fuse = !(flags & GML_F_FORCE_STREAMING) && la && lb &&
+  const size_t tile_bytes = (d.c_v == d.c_s && d.hw_v == d.hw_s) ? tile_bwd_workspace_bytes(d.n, d.c_v, d.hw_v, d.d) : 0;
+  const bool can_tile = !(flags & (GML_F_FORCE_STREAMING | GML_F_FORCE_FUSED)) && la && lb && tile_bytes &&
+                        tile_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
+  if ((flags & GML_F_FORCE_TILE) && !can_tile) return GML_E_UNSUPPORTED;
+  bool tiled = false;
+  if (can_tile && ((flags & GML_F_FORCE_TILE) || tile_preferred(d.n, d.c_v, d.hw_v, d.d))) {
+    FusedBwdArgs fb{go_a, go_b, a, b, w_sq, w_v, w_s, z, h, g_a, g_b, run_v, run_s, d_a, d_b, de_a, de_b, dh,
+                    d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
+    const int rc = launch_tile_bwd(fb, dz, d_b_v, d_b_s, d_b_sq, tile_ws, tile_bytes, st);
+    if (rc == GML_OK) { tiled = true; bias_done = true; }
+    else if (rc != GML_E_UNSUPPORTED || (flags & GML_F_FORCE_TILE)) return rc;
+  }
+
+  const bool can_fuse = !tiled && !(flags & (GML_F_FORCE_STREAMING | GML_F_FORCE_TILE)) && la && lb &&
                         fused_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
   if ((flags & GML_F_FORCE_FUSED) && !can_fuse) return GML_E_UNSUPPORTED;
-  if (can_fuse) {
+  if (tiled) {
+    // d_input, dE, dH and the bias gradients are done; the weight-gradient GEMMs follow below
+  } else if (can_fuse) {
     FusedBwdArgs fb{go_a, go_b, a, b, w_sq, w_v, w_s, z, h, g_a, g_b, run_v, run_s, d_a, d_b, de_a, de_b, dh,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
     GML_TRY(launch_fused_bwd(fb, st));

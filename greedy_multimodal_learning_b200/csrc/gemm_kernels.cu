@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "umma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -45,14 +46,6 @@ struct PipeBatch {
   int k_per_split;       // multiple of BK
   long long* trace;      // debug: phase stamps of CTA (0,0,0) of the tcgen05 kernel, or nullptr
 };
-
-__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int src_bytes) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // one operand tile for k in [k0, k0 + BK): KC = k-contiguous source (src[t * ld + k]), else src[k * ld + t]
 template <bool KC, int BT, int PITCH_MN = TileGeom<BT>::kPitchMN>
@@ -460,148 +453,6 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_mma_kernel(const PipeBatch pb
 //     four lanes that hold k..k+3 (two shuffle rounds) into K-major chunks, split and stored.
 // Every lane group of 8 touches 8 different bank groups and every global read is a 64-byte run.
 // -----------------------------------------------------------------------------------------------
-constexpr int UM = 128, UN = 128, UK = 32, USTAGES = 3, UGROUP = 4;
-constexpr int U_PRODUCERS = 256, UTHREADS = U_PRODUCERS + 32;
-constexpr int U_TILE_BYTES = UM * UK * 4;        // 16 KB
-constexpr int U_STAGE_BYTES = 4 * U_TILE_BYTES;  // A big | A small | B big | B small
-constexpr uint32_t U_TMEM_COLS = 256;            // two accumulators of 128 lanes x 128 fp32 columns
-
-__device__ __forceinline__ uint32_t u_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void u_mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(u_smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void u_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spins = 0; !ok; ++spins) {  // bounded: a lost completion must trap, never hang the GPU
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(u_smem_addr(bar)), "r"(parity)
-        : "memory");
-    if (!ok && spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void u_commit(uint64_t* bar) {
-  // arrives on the barrier once every MMA this thread has issued so far is complete
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ uint64_t u_desc(uint32_t addr) {
-  // start address [0,14) >> 4; leading byte offset [16,30) unused for swizzled K-major (1); stride byte offset
-  // [32,46) = 1024 >> 4; descriptor version 1 at [46,48); layout type SWIZZLE_128B (2) at [61,64)
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void u_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void u_tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// byte offset of chunk kc of row t in the swizzled K-major tile
-__device__ __forceinline__ uint32_t u_kmajor_off(int t, int kc) {
-  return (uint32_t)((t >> 3) * 1024 + (t & 7) * 128 + ((kc ^ (t & 7)) << 4));
-}
-constexpr int U_MN_PITCH = UM + 4;  // floats per k row of an MN-major landing zone (16-byte aligned rows; a column
-                                    // walk of 4 k then touches banks 4 apart -> conflict-free with the lane map below)
-// K-major source: chunk i of a producer thread is row t, k-chunk kc; it lands at its final (swizzled) offset.
-template <bool KC>
-__device__ __forceinline__ void u_chunk(int i, int warp, int lane, int& t, int& kc) {
-  const int wc = warp + 8 * i;
-  if (KC) {  // 8 rows x 4 k-chunks per warp: 64-byte global runs, one swizzle atom row group per 8 lanes
-    kc = (wc >> 4) * 4 + (lane >> 3);
-    t = (wc & 15) * 8 + (lane & 7);
-  } else {   // final chunks of an MN-major source: 16 rows x 2 k-chunks per warp (see u_read_chunks)
-    kc = (wc >> 3) * 2 + (lane >> 4);
-    t = (wc & 7) * 16 + (lane & 15);
-  }
-}
-template <bool KC>
-__device__ __forceinline__ void u_load_tile(unsigned char* tile, const float* __restrict__ src, int ld, int t0, int tmax,
-                                            int k0, int kmax, int warp, int lane) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int bytes;
-    const float* g;
-    uint32_t land;
-    if (KC) {
-      int t, kc;
-      u_chunk<true>(i, warp, lane, t, kc);
-      land = u_kmajor_off(t, kc);
-      t += t0;
-      const int k = k0 + kc * 4;
-      bytes = (t < tmax) ? (kmax - k) * 4 : 0;
-      g = src + (size_t)t * ld + k;
-    } else {  // k row `kr`, 4 consecutive t: one warp covers a whole 512-byte row of the tile
-      const int kr = warp + 8 * i, tc = lane;
-      land = (uint32_t)((kr * U_MN_PITCH + tc * 4) * 4);
-      const int k = k0 + kr, t = t0 + tc * 4;
-      bytes = (k < kmax) ? (tmax - t) * 4 : 0;
-      g = src + (size_t)k * ld + t;
-    }
-    bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-    cp_async16(reinterpret_cast<float*>(tile + land), bytes > 0 ? g : src, bytes);
-  }
-}
-// K-major: my own chunks back from where cp.async put them.  MN-major: the landing zone holds [k][t]; chunk
-// (t, kc) is the column walk k = 4 kc .. 4 kc + 3 at fixed t -- 16 lanes on 16 consecutive t, the two lane halves
-// 4 k rows (16 banks) apart: conflict-free.  (Needs a barrier first: other threads loaded those rows.)
-template <bool KC>
-__device__ __forceinline__ void u_read_chunks(const unsigned char* tile, int warp, int lane, float4 (&x)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int t, kc;
-    u_chunk<KC>(i, warp, lane, t, kc);
-    if (KC) {
-      x[i] = *reinterpret_cast<const float4*>(tile + u_kmajor_off(t, kc));
-    } else {
-      const float* col = reinterpret_cast<const float*>(tile) + (kc * 4) * U_MN_PITCH + t;
-      x[i] = make_float4(col[0], col[U_MN_PITCH], col[2 * U_MN_PITCH], col[3 * U_MN_PITCH]);
-    }
-  }
-}
-// big (in place for K-major sources, where the raw chunk already sits at its final offset and the tensor core
-// reads only the top 19 bits of each word, i.e. sees exactly x & ~0x1fff) and small = x - big (twin tile)
-template <bool KC>
-__device__ __forceinline__ void u_write_split(unsigned char* big_tile, unsigned char* small_tile, int warp, int lane,
-                                              const float4 (&x)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int t, kc;
-    u_chunk<KC>(i, warp, lane, t, kc);
-    const uint32_t fin = u_kmajor_off(t, kc);
-    const float4 v = x[i];
-    float4 b, s;
-    b.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); s.x = v.x - b.x;
-    b.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); s.y = v.y - b.y;
-    b.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); s.z = v.z - b.z;
-    b.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); s.w = v.w - b.w;
-    if (!KC) *reinterpret_cast<float4*>(big_tile + fin) = b;
-    *reinterpret_cast<float4*>(small_tile + fin) = s;
-  }
-}
-
 template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(UTHREADS, 1) gemm_umma_kernel(const PipeBatch pb) {
   extern __shared__ __align__(1024) unsigned char u_smem_raw[];

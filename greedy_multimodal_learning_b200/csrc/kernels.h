@@ -117,4 +117,17 @@ bool fused_fwd_preferred(int n, int c, int hw, int d);
 int launch_fused_fwd(const FusedFwdArgs& args, cudaStream_t st);
 int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st);
 
+
+// ---- tile pipeline (tile_kernels.cu): one persistent kernel per block and direction, normal mode -----------------
+bool tile_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mode);
+bool tile_preferred(int n, int c, int hw, int d);
+size_t tile_fwd_workspace_bytes(int n, int c, int hw, int d);
+size_t tile_bwd_workspace_bytes(int n, int c, int hw, int d);
+// gate_sum / run_v / run_s may be nullptr (no column sum / no running-mean update inside the kernel)
+int launch_tile_fwd(const FusedFwdArgs& args, float* gate_sum, float* run_v, float* run_s, float step, void* ws,
+                    size_t ws_bytes, cudaStream_t st);
+// dz_flat: [2, N, C] scratch; d_b_*: bias gradients (column sums of dE_a, dE_b, dH) or nullptr
+int launch_tile_bwd(const FusedBwdArgs& args, float* dz_flat, float* d_b_v, float* d_b_s, float* d_b_sq, void* ws,
+                    size_t ws_bytes, cudaStream_t st);
+
 }  // namespace gml

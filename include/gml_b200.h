@@ -49,7 +49,8 @@ extern "C" {
 #define GML_F_NO_RUNNING_UPDATE 1u /* skip the running-mean update (data-parallel callers do
                                       it themselves after all-reducing gate_sum)             */
 #define GML_F_FORCE_STREAMING 2u   /* never pick the cluster/shared-memory-resident kernels  */
-#define GML_F_FORCE_FUSED 4u       /* fail with GML_E_UNSUPPORTED instead of falling back    */
+#define GML_F_FORCE_FUSED 4u       /* cluster kernels or GML_E_UNSUPPORTED, never a fallback  */
+#define GML_F_FORCE_TILE 8u        /* tile-pipeline kernel or GML_E_UNSUPPORTED               */
 
 /* learning-speed buckets (src/callbacks.py:207-223); a tensor may feed several */
 #define GML_BUCKET_MAIN0 1
@@ -95,6 +96,10 @@ int gml_profile_read(int tag, double* total_ms, int64_t* launches);
  *   "gemm_umma"      1 tcgen05 (TMEM) 3xTF32 kernel for FC problems above ~1e8 MACs | 0 never
  *   "gemm_tf32x3"    1 mma.sync 3xTF32 for large problems the tcgen05 kernel does not take | 0 CUDA cores
  *   "gemm_big_tiles" 1 opt-in 128x128 CUDA-core tiles
+ *   "tile_kind"      0 auto | 1 tile pipeline whenever the shape allows | 2 never
+ *   "tile_lag", "tile_m", "tile_gemm_ctas", "tile_chunk_kb", "tile_min_mb"
+ *                    pipeline depth in tiles / samples per tile / CTAs on the FC role / chunk size /
+ *                    smallest feature map (MB per modality) that takes the tile pipeline automatically
  *   "overlap_wgrad"  1 weight-gradient GEMMs on the library's side stream (streaming backward)
  *   "fused_trace_ptr", "gemm_trace_ptr"  device buffers for per-phase timing stamps (debug)        */
 int gml_set_tunable(const char* name, int64_t value);
