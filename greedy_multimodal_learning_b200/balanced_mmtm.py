@@ -210,7 +210,15 @@ class MMTM_mitigate(nn.Module):
             m_a = average_squeezemaps[0].detach().to(device=dev, dtype=torch.float32).contiguous()
             m_b = average_squeezemaps[1].detach().to(device=dev, dtype=torch.float32).contiguous()
         if visual.shape[0] == 0:
-            # empty batch: nothing to launch (the reference would produce NaN running means here)
+            # empty batch: nothing to launch (the reference would produce NaN running means here).  Under data
+            # parallelism the other ranks are inside the gate-sum all-reduce: join it with zeros and a count of 0
+            grp = self._dist_group()
+            if grp is not None:
+                gs = torch.zeros(self.dim_visual + 1, dtype=torch.float32, device=dev)
+                torch.distributed.all_reduce(gs, group=grp)
+                _MMTMFunction._running_update_dp(self.running_avg_weight_visual, self.running_avg_weight_skeleton,
+                                                 gs[:self.dim_visual], gs[self.dim_visual], self.step)
+                self.step += 1
             return visual.clone(), skeleton.clone(), None, None
         a, b = visual.contiguous(), skeleton.contiguous()
         # the reference rebinds running_avg_* to fresh tensors every call (:113-114); keep that

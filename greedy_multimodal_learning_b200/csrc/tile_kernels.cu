@@ -29,6 +29,8 @@
 //
 // Replaces, for mode 0: reference src/balanced_mmtm.py:93-111,128-133,154 (forward) and the autograd graph of those
 // lines (backward).
+#include <cuda.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -43,6 +45,7 @@ int g_tile_gemm_ctas = 0;   // tunable "tile_gemm_ctas": 0 = from the FLOP/byte 
 int g_tile_m = 0;           // tunable "tile_m": samples per tile, 0 = automatic (~25 MB of feature map per tile)
 int g_tile_chunk_kb = 28;   // tunable "tile_chunk_kb": upper bound of a chunk (one work item) in KB
 int g_tile_min_mb = 8;      // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality
+long long* g_tile_stats = nullptr;  // debug: per-CTA cycle breakdown (device buffer, 16 slots per CTA)
 
 namespace {
 
@@ -59,10 +62,12 @@ enum { kItemR = 0, kItemS = 1, kItemStop = 2 };
 enum { kEpiRelu = 0, kEpiSigmoid = 1, kEpiMask = 2, kEpiDiv = 3 };
 
 struct GemmStage {
-  const float* a; const float* a2;   // A rows = samples, K-major; k >= k_split comes from a2 (k - k_split)
-  int lda, lda2, k_split;
-  const float* b; const float* b2;   // B rows = output columns, K-major; rows >= n_split come from b2 (n - n_split)
-  int ldb, n_split;
+  // operands as TMA tensor maps (fp32 [rows, K], box 32 k x 32 rows, SWIZZLE_128B = the canonical K-major UMMA layout)
+  alignas(64) CUtensorMap tm_a;    // A rows = samples
+  alignas(64) CUtensorMap tm_a2;   // k >= k_split comes from here (k - k_split)
+  alignas(64) CUtensorMap tm_b;    // B rows = output columns
+  alignas(64) CUtensorMap tm_b2;   // rows >= n_split come from here (n - n_split)
+  int k_split, n_split;
   int n_total, k_total;
   int n_tiles, splits, k_per_split;  // k_per_split is a multiple of UK
   float* out; float* out2;           // column < n_split -> out[row * ldo + col], else out2[row * ldo + col - n_split]
@@ -92,13 +97,14 @@ struct TileParams {
   const float* w_v; const float* w_s; const float* w_sq;
   float* w_cat_t; float* w_sq_t;   // [D, 2C], [2C, D]; nullptr in the forward
   int n, c, hw, d, bwd;
-  int m_tile, n_tiles, p, lanes, lag, n_gemm;
-  int slots, nbuf;
+  int m_tile, n_tiles, p, lanes, lanes_log2, lag, n_gemm;
+  int slots, wps, nbuf;      // slots is a power of two <= 8; wps = 8 / slots worker warps serve one slot
   uint32_t chunk_bytes, slot_bytes, hw_magic;
   float gate_scale;
   unsigned* ctr;
   float* part;
   size_t part_tile_floats;   // partial planes of one tile: (sum over stages of n_tiles * splits) * 128 * 128
+  long long* stats;          // debug (tunable "tile_stats_ptr"): 16 clock64 sums per CTA, or nullptr
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------------
@@ -109,6 +115,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// cycle counter the compiler may not move memory operations across (debug statistics)
+__device__ __forceinline__ long long clk() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
 }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -139,7 +151,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ float ldcg_f32(const float* p) { return __ldcg(p); }
 
-struct SlotMeta { int kind, mod, tile, q0; };
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(u_smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+struct SlotMeta { int kind, mod, tile, q0, rofs, pad0, pad1, pad2; };  // rofs: offset of the chunk's first R result
 
 __device__ __forceinline__ int tile_rows(const TileParams& P, int t) {
   const int r = P.n - t * P.m_tile;
@@ -164,7 +188,11 @@ struct StreamSmem {
   __device__ __forceinline__ float* add(int slot, int nbuf) const { return gate(slot, nbuf) + p; }
 };
 
-__device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMeta* metas, uint64_t* full, uint64_t* empty) {
+// The loader also signals R-stage completion: a slot's `empty` barrier tells it that all eight worker warps are done
+// with the item that occupied the slot, so it can add this CTA's finished R items of a tile to the tile's global
+// counter with ONE release per (CTA, tile) instead of a gpu-scope fence per warp and item.
+__device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMeta* metas, uint64_t* full, uint64_t* empty,
+                              long long* st_cycles) {
   const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
   const int T = P.n_tiles, nseg = 2 * (T + P.lag);
   const size_t planes_per_tile = (size_t)P.m_tile * P.c;
@@ -176,23 +204,70 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
     if (t < 0 || t >= T) return 0u;
     return 2u * (unsigned)((size_t)tile_rows(P, t) * P.c / P.p);
   };
-  unsigned uses = 0;
+  unsigned uses = 0;       // items issued so far; item u lives in slot u % slots
+  unsigned retired = 0;    // items [0, retired) are known to be finished by all worker warps
   int slot = 0;
   const unsigned need_f2 = (unsigned)P.st[1].n_tiles;
+  // R bookkeeping, indexed by tile & 15 (at most `slots` <= 8 different tiles can be in flight)
+  int rec_tile[kMaxSlots];               // tile of the R item in a slot, -1 for S
+  unsigned short issued[16], done[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { issued[i] = 0; done[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < kMaxSlots; ++i) rec_tile[i] = -1;
+  int flush_tile = 0;                    // lowest tile whose R count this CTA has not published yet
+  long long c_empty = 0, c_dep = 0;
+
+  // items [retired, upto) -> wait for their workers, account finished R items
+  auto retire = [&](unsigned upto) {
+    while (retired < upto) {
+      const int s_ = (int)(retired % (unsigned)P.slots);
+      u_mbar_wait(&empty[s_], (retired / (unsigned)P.slots) & 1u);
+      if (rec_tile[s_] >= 0) done[rec_tile[s_] & 15]++;
+      ++retired;
+    }
+  };
+  // the same without blocking: whatever the workers have finished by now
+  auto retire_ready = [&]() {
+    while (retired < uses) {
+      const int s_ = (int)(retired % (unsigned)P.slots);
+      if (!mbar_test(&empty[s_], (retired / (unsigned)P.slots) & 1u)) break;
+      if (rec_tile[s_] >= 0) done[rec_tile[s_] & 15]++;
+      ++retired;
+    }
+  };
+  // publish every tile whose R items (of this CTA) are all issued and finished
+  auto flush = [&](bool exhausted) {
+    while (flush_tile < T && (exhausted || seg > 2 * flush_tile) && done[flush_tile & 15] == issued[flush_tile & 15]) {
+      if (issued[flush_tile & 15]) red_release_add(tile_ctr(P, flush_tile) + 0, (unsigned)issued[flush_tile & 15]);
+      issued[flush_tile & 15] = 0; done[flush_tile & 15] = 0;
+      ++flush_tile;
+    }
+  };
+
   // tickets are drawn two at a time and one draw ahead: the atomic's round trip overlaps the current items
   unsigned cur = atomicAdd(&P.ctr[0], 2u);
   for (;;) {
     const unsigned nxt = atomicAdd(&P.ctr[0], 2u);
     for (unsigned ticket = cur; ticket < cur + 2u; ++ticket) {
       while (seg < nseg && ticket >= seg_start + seg_size(seg)) { seg_start += seg_size(seg); ++seg; }
-      if (uses >= (unsigned)P.slots) u_mbar_wait(&empty[slot], ((uses / P.slots) - 1u) & 1u);
-      SlotMeta m;
-      if (seg >= nseg) {  // queue exhausted: tell the workers
-        m.kind = kItemStop; m.mod = 0; m.tile = 0; m.q0 = 0;
-        metas[slot] = m;
-        u_mbar_arrive(&full[slot]);
+      if (seg >= nseg) {  // queue exhausted: finish the bookkeeping, then tell the workers
+        retire(uses);
+        flush(true);
+        for (int s_ = 0; s_ < P.slots; ++s_) {  // every slot has its own worker warps
+          metas[s_].kind = kItemStop;
+          u_mbar_arrive(&full[s_]);
+        }
+        if (st_cycles) { st_cycles[2] = c_empty; st_cycles[3] = c_dep; st_cycles[1] = uses; }
         return;
       }
+      const long long t0 = st_cycles ? clk() : 0;
+      if (uses >= (unsigned)P.slots) retire(uses - (unsigned)P.slots + 1u);  // frees this item's slot
+      retire_ready();
+      if (!(seg & 1) && seg_tile(seg) - flush_tile >= 15) retire(uses);  // keep the & 15 bookkeeping window valid
+      flush(false);
+      const long long t1 = st_cycles ? clk() : 0;
+      SlotMeta m;
       const int t = seg_tile(seg);
       const unsigned idx = ticket - seg_start;
       const unsigned chunks = (unsigned)((size_t)tile_rows(P, t) * P.c / P.p);
@@ -200,11 +275,25 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
       m.mod = idx >= chunks ? 1 : 0;
       m.tile = t;
       m.q0 = (int)((size_t)t * planes_per_tile + (size_t)(idx - (m.mod ? chunks : 0u)) * P.p);
+      {  // first plane of the chunk = sample n, channel c0 (a chunk never straddles samples: P divides C)
+        const int n_ = m.q0 / P.c;
+        m.rofs = n_ * P.rout_ld + (m.q0 - n_ * P.c);
+      }
+      m.pad0 = m.pad1 = m.pad2 = 0;
       if (m.kind == kItemS) {
-        wait_counter(tile_ctr(P, t) + 2, need_f2);
+        if (ld_acquire_u32(tile_ctr(P, t) + 2) < need_f2) {
+          // about to block: everything this CTA still owes the R counters must be published first
+          retire(uses);
+          flush(false);
+          wait_counter(tile_ctr(P, t) + 2, need_f2);
+        }
         asm volatile("fence.proxy.async;" ::: "memory");  // the gates were written through the generic proxy
       }
+      const long long t2 = st_cycles ? clk() : 0;
+      c_empty += t1 - t0; c_dep += t2 - t1;
       metas[slot] = m;
+      rec_tile[slot] = m.kind == kItemR ? t : -1;
+      if (m.kind == kItemR) issued[t & 15]++;
       const size_t off = (size_t)m.q0 * P.hw;
       const uint32_t vec_bytes = (uint32_t)P.p * 4u;
       if (m.kind == kItemR) {
@@ -230,16 +319,18 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
   }
 }
 
-// plane sums (forward) or <grad_out, input> dots (backward) of the P planes of a chunk
+// A slot is served by `wps` worker warps (one warp per slot when the ring has 8 slots): different warps work on
+// different items at the same time, so whatever one warp waits for (its result stores before the releasing arrive,
+// shared-memory latency) is hidden behind the other slots' warps.
+//
+// plane sums (forward) or <grad_out, input> dots (backward) of the P planes of a chunk; L lanes per plane
 __device__ __forceinline__ void reduce_chunk(const TileParams& P, const SlotMeta& m, const float* b0, const float* b1,
-                                             const float* sgate, int tid) {
-  const int L = P.lanes, lane_in = tid & (L - 1), grp = tid / L, ngrp = U_PRODUCERS / L;
+                                             const float* sgate, int sw, int lane) {
+  const int L = P.lanes, lane_in = lane & (L - 1), gpw = 32 >> P.lanes_log2, grp = lane >> P.lanes_log2;
   const int hw = P.hw;
-  // first plane of the chunk: sample n, channel c0 (a chunk never straddles samples: P divides C)
-  const int n = m.q0 / P.c, c0 = m.q0 - n * P.c;
-  float* dst = P.rout[m.mod] + (size_t)n * P.rout_ld + c0;
-  // the trip count is uniform over the CTA (shuffles below): inactive groups run with `act == false`
-  for (int base = 0; base < P.p; base += ngrp) {
+  float* dst = P.rout[m.mod] + m.rofs;
+  // the trip count is uniform over the warp (shuffles below): inactive groups run with `act == false`
+  for (int base = sw * gpw; base < P.p; base += P.wps * gpw) {
     const int pl = base + grp;
     const bool act = pl < P.p;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -247,18 +338,29 @@ __device__ __forceinline__ void reduce_chunk(const TileParams& P, const SlotMeta
       if ((hw & 3) == 0) {
         const int hw4 = hw >> 2;
         const float4* v = reinterpret_cast<const float4*>(b0) + (size_t)pl * hw4;
+        int i = lane_in;
         if (P.bwd) {
           const float4* w = reinterpret_cast<const float4*>(b1) + (size_t)pl * hw4;
-#pragma unroll 4
-          for (int i = lane_in; i < hw4; i += L) {
-            const float4 g = v[i], x = w[i];
-            a0 = fmaf(g.x, x.x, a0); a1 = fmaf(g.y, x.y, a1); a2 = fmaf(g.z, x.z, a2); a3 = fmaf(g.w, x.w, a3);
+          for (; i + L < hw4; i += 2 * L) {
+            const float4 g0 = v[i], x0 = w[i], g1 = v[i + L], x1 = w[i + L];
+            a0 = fmaf(g0.x, x0.x, a0); a1 = fmaf(g0.y, x0.y, a1); a2 = fmaf(g0.z, x0.z, a2); a3 = fmaf(g0.w, x0.w, a3);
+            a0 = fmaf(g1.x, x1.x, a0); a1 = fmaf(g1.y, x1.y, a1); a2 = fmaf(g1.z, x1.z, a2); a3 = fmaf(g1.w, x1.w, a3);
+          }
+          if (i < hw4) {
+            const float4 g0 = v[i], x0 = w[i];
+            a0 = fmaf(g0.x, x0.x, a0); a1 = fmaf(g0.y, x0.y, a1); a2 = fmaf(g0.z, x0.z, a2); a3 = fmaf(g0.w, x0.w, a3);
           }
         } else {
-#pragma unroll 4
-          for (int i = lane_in; i < hw4; i += L) {
-            const float4 x = v[i];
-            a0 += x.x; a1 += x.y; a2 += x.z; a3 += x.w;
+          for (; i + 3 * L < hw4; i += 4 * L) {
+            const float4 x0 = v[i], x1 = v[i + L], x2 = v[i + 2 * L], x3 = v[i + 3 * L];
+            a0 += x0.x; a1 += x0.y; a2 += x0.z; a3 += x0.w;
+            a0 += x1.x; a1 += x1.y; a2 += x1.z; a3 += x1.w;
+            a0 += x2.x; a1 += x2.y; a2 += x2.z; a3 += x2.w;
+            a0 += x3.x; a1 += x3.y; a2 += x3.z; a3 += x3.w;
+          }
+          for (; i < hw4; i += L) {
+            const float4 x0 = v[i];
+            a0 += x0.x; a1 += x0.y; a2 += x0.z; a3 += x0.w;
           }
         }
       } else {
@@ -297,15 +399,16 @@ __device__ __forceinline__ int plane_of(unsigned e, const TileParams& P) {
 
 // out = x * (gate * gate_scale) [+ add]: flat 128-bit walk over the chunk, the plane of an element from its index
 __device__ __forceinline__ void scale_chunk(const TileParams& P, const SlotMeta& m, const float* b0, const float* sgate,
-                                            const float* sadd, int tid) {
+                                            const float* sadd, int sw, int lane) {
   const int hw = P.hw;
   const int nvec = (int)(P.chunk_bytes >> 4);
+  const int step = 32 * P.wps;
   const float4* v = reinterpret_cast<const float4*>(b0);
   float4* o = reinterpret_cast<float4*>(P.out[m.mod] + (size_t)m.q0 * hw);
   const float gs = P.gate_scale;
   if ((hw & 3) == 0) {
-#pragma unroll 2
-    for (int i = tid; i < nvec; i += U_PRODUCERS) {
+#pragma unroll 4
+    for (int i = sw * 32 + lane; i < nvec; i += step) {
       const int pl = plane_of((unsigned)(4 * i), P);
       const float sc = sgate[pl] * gs;
       float4 x = v[i];
@@ -319,7 +422,7 @@ __device__ __forceinline__ void scale_chunk(const TileParams& P, const SlotMeta&
     }
   } else {
 #pragma unroll 2
-    for (int i = tid; i < nvec; i += U_PRODUCERS) {
+    for (int i = sw * 32 + lane; i < nvec; i += step) {
       const unsigned e = 4u * (unsigned)i;
       const int p0 = plane_of(e, P), p1 = plane_of(e + 1, P), p2 = plane_of(e + 2, P), p3 = plane_of(e + 3, P);
       float4 x = v[i];
@@ -334,69 +437,101 @@ __device__ __forceinline__ void scale_chunk(const TileParams& P, const SlotMeta&
   }
 }
 
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(u_smem_addr(bar)) : "memory");
+}
+
 __device__ void stream_workers(const TileParams& P, const StreamSmem& sm, const SlotMeta* metas, uint64_t* full,
-                               uint64_t* empty, int tid) {
-  const int lane = tid & 31;
-  int slot = 0;
+                               uint64_t* empty, int tid, long long* st_cycles) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int slot = warp / P.wps, sw = warp - slot * P.wps;
   uint32_t phase = 0;
+  long long c_wait = 0, c_red = 0, c_scale = 0;
+  const bool timing = st_cycles != nullptr && tid == 0;
   for (;;) {
+    const long long t0 = timing ? clk() : 0;
     u_mbar_wait(&full[slot], phase);
+    const long long t1 = timing ? clk() : 0;
     const SlotMeta m = metas[slot];
-    if (m.kind == kItemStop) return;
+    if (m.kind == kItemStop) break;
     if (m.kind == kItemR) {
-      reduce_chunk(P, m, sm.chunk(slot, 0), sm.chunk(slot, 1), sm.gate(slot, P.nbuf), tid);
+      reduce_chunk(P, m, sm.chunk(slot, 0), sm.chunk(slot, 1), sm.gate(slot, P.nbuf), sw, lane);
       __syncwarp();
-      if (lane == 0) {
-        u_mbar_arrive(&empty[slot]);
-        red_release_add(tile_ctr(P, m.tile) + 0, 1u);  // 8 arrivals (one per worker warp) per R item
-      }
+      if (lane == 0) u_mbar_arrive(&empty[slot]);  // release.cta: the loader publishes the R results after its wait
     } else {
-      scale_chunk(P, m, sm.chunk(slot, 0), sm.gate(slot, P.nbuf), sm.add(slot, P.nbuf), tid);
+      scale_chunk(P, m, sm.chunk(slot, 0), sm.gate(slot, P.nbuf), sm.add(slot, P.nbuf), sw, lane);
       __syncwarp();
-      if (lane == 0) u_mbar_arrive(&empty[slot]);
+      // nothing to publish: the arrival only says that this warp's shared-memory reads are done (their values
+      // have been consumed by the stores issued above)
+      if (lane == 0) mbar_arrive_relaxed(&empty[slot]);
     }
-    if (++slot == P.slots) { slot = 0; phase ^= 1u; }
+    if (timing) {
+      const long long t2 = clk();
+      c_wait += t1 - t0;
+      if (m.kind == kItemR) c_red += t2 - t1; else c_scale += t2 - t1;
+    }
+    phase ^= 1u;
   }
+  if (timing) { st_cycles[4] = c_wait; st_cycles[5] = c_red; st_cycles[6] = c_scale; }
 }
 
 // =================================================================================================================
 // GEMM role
 // =================================================================================================================
-struct GemmBars { uint64_t* full; uint64_t* empty; uint64_t* acc_full; uint64_t* acc_empty; };
+struct GemmBars { uint64_t* raw; uint64_t* full; uint64_t* empty; uint64_t* acc_full; uint64_t* acc_empty; };
 
 struct GemmItem { int stage, tile, ntile, split; };
 
-// K-major operand tile (128 rows x 32 k) via cp.async, rows resolved by `rowptr` (nullptr -> zero fill)
-template <typename RowPtr>
-__device__ __forceinline__ void t_load_tile(unsigned char* tile, RowPtr rowptr, const float* dummy, int t0, int k0,
-                                            int kmax, int warp, int lane) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int t, kc;
-    u_chunk<true>(i, warp, lane, t, kc);
-    const uint32_t land = u_kmajor_off(t, kc);
-    const float* row = rowptr(t0 + t);
-    const int k = k0 + kc * 4;
-    int bytes = row ? (kmax - k) * 4 : 0;
-    bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-    cp_async16(reinterpret_cast<float*>(tile + land), bytes > 0 ? row + k : dummy, bytes);
-  }
+// 2-D TMA tile load: box (32 k x 32 rows) of an fp32 [rows, K] tensor -> shared memory, SWIZZLE_128B
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int k, int row, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          u_smem_addr(dst)),
+      "l"(map), "r"(k), "r"(row), "r"(u_smem_addr(bar))
+      : "memory");
 }
 
 // One 128 x 128 x [k0, k1) product on tcgen05 (3xTF32).  Workers leave with the fp32 result of their row x 64
 // columns in `sum`.  kbase / gbase: k-tiles and accumulator groups this CTA has pushed through its barriers so far.
+//
+// Per k-tile of 32: the control thread (warp 8) fetches the raw fp32 operand tiles with TMA (tensor maps with
+// SWIZZLE_128B write the canonical K-major UMMA layout directly, out-of-range rows / k arrive as zeros); the raw tile IS
+// the "big" TF32 operand (the tensor core reads the top 19 bits of each word); the 256 workers only compute the
+// "small" twin (x - trunc(x)) and hand the stage to the MMA issue.  No thread that fences (fence.proxy.async is a
+// MEMBAR) has global loads in flight, so the TMA prefetch of the next stages is never serialised.
 __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const GemmStage& g, const GemmItem& it,
                                                    unsigned char* u_smem, const GemmBars& bars, uint32_t tmem,
                                                    uint32_t kbase, uint32_t gbase, int nk, float (&sum)[64], int warp,
-                                                   int lane) {
-  const int m0 = it.tile * P.m_tile, m_end = m0 + tile_rows(P, it.tile);
+                                                   int lane, int tid) {
+  const int m0 = it.tile * P.m_tile;
   const int n0 = it.ntile * UN;
   const int k_begin = it.split * g.k_per_split;
-  const int k_end = min(g.k_total, k_begin + g.k_per_split);
   if (warp == U_PRODUCERS / 32) {
-    // ===== MMA issuer ==========================================================================================
+    // ===== control thread: TMA producer + MMA issuer ============================================================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+      auto issue_tma = [&](int kt) {
+        const uint32_t KT = kbase + (uint32_t)kt, stage = KT % USTAGES;
+        // the stage was last read by the MMAs of k-tile KT - USTAGES
+        if (KT >= (uint32_t)USTAGES) u_mbar_wait(&bars.empty[stage], ((KT / USTAGES) - 1u) & 1u);
+        unsigned char* st = u_smem + stage * U_STAGE_BYTES;
+        mbar_expect_tx(&bars.raw[stage], 2u * U_TILE_BYTES);
+        const int k0 = k_begin + kt * UK;
+        const bool second = g.k_split && k0 >= g.k_split;
+        const CUtensorMap* ma = second ? &g.tm_a2 : &g.tm_a;
+        const int ka = second ? k0 - g.k_split : k0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_2d(st + j * 4096, ma, ka, m0 + 32 * j, &bars.raw[stage]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = n0 + 32 * j;
+          const bool hi = r >= g.n_split;
+          tma_load_2d(st + 2 * U_TILE_BYTES + j * 4096, hi ? &g.tm_b2 : &g.tm_b, k0, hi ? r - g.n_split : r,
+                      &bars.raw[stage]);
+        }
+      };
+      const int npre = nk < USTAGES ? nk : USTAGES;
+      for (int s = 0; s < npre; ++s) issue_tma(s);
       for (int kt = 0; kt < nk; ++kt) {
         const uint32_t KT = kbase + (uint32_t)kt, GI = gbase + (uint32_t)(kt / UGROUP);
         const uint32_t stage = KT % USTAGES, b = GI & 1u;
@@ -417,12 +552,14 @@ __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const Ge
         }
         u_commit(&bars.empty[stage]);
         if (kt % UGROUP == UGROUP - 1 || kt == nk - 1) u_commit(&bars.acc_full[b]);
+        // refill the stage of the PREVIOUS k-tile (its MMAs finish while the ones just queued run)
+        if (kt >= 1 && kt - 1 + USTAGES < nk) issue_tma(kt - 1 + USTAGES);
       }
     }
     __syncwarp();
     return;
   }
-  // ===== producers / drainers ==================================================================================
+  // ===== workers: operand split + accumulator drain ==============================================================
 #pragma unroll
   for (int i = 0; i < 64; ++i) sum[i] = 0.f;
   const int ngroups = (nk + UGROUP - 1) / UGROUP;
@@ -442,91 +579,73 @@ __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const Ge
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     u_mbar_arrive(&bars.acc_empty[b]);
   };
-  auto issue_loads = [&](int kt) {
-    const uint32_t KT = kbase + (uint32_t)kt;
-    // the stage was last read by the MMAs of k-tile KT - USTAGES
-    if (KT >= (uint32_t)USTAGES) u_mbar_wait(&bars.empty[KT % USTAGES], ((KT / USTAGES) - 1u) & 1u);
-    unsigned char* st = u_smem + (KT % USTAGES) * U_STAGE_BYTES;
-    const int k0 = k_begin + kt * UK;
-    // A: second K segment from a2
-    const bool second = g.k_split && k0 >= g.k_split;
-    const float* abase = second ? g.a2 : g.a;
-    const int lda = second ? g.lda2 : g.lda;
-    const int ka = second ? k0 - g.k_split : k0;
-    const int kamax = second ? k_end - g.k_split : (g.k_split ? min(k_end, g.k_split) : k_end);
-    t_load_tile(st, [&](int r) { return r < m_end ? abase + (size_t)r * lda : (const float*)nullptr; }, g.a, m0, ka,
-                kamax, warp, lane);
-    t_load_tile(st + 2 * U_TILE_BYTES,
-                [&](int r) {
-                  return r < g.n_split ? g.b + (size_t)r * g.ldb
-                                       : (r < g.n_total ? g.b2 + (size_t)(r - g.n_split) * g.ldb : (const float*)nullptr);
-                },
-                g.a, n0, k0, k_end, warp, lane);
-  };
-#pragma unroll
-  for (int s = 0; s < USTAGES - 1; ++s) {
-    if (s < nk) issue_loads(s);
-    cp_async_commit();
-  }
   for (int kt = 0; kt < nk; ++kt) {
-    const int nxt = kt + USTAGES - 1;
-    if (nxt < nk) issue_loads(nxt);
-    cp_async_commit();
-    cp_async_wait<USTAGES - 1>();  // my chunks of k-tile kt have landed
-    const uint32_t KT = kbase + (uint32_t)kt;
-    unsigned char* st = u_smem + (KT % USTAGES) * U_STAGE_BYTES;
-    float4 xa[4], xb[4];
-    u_read_chunks<true>(st, warp, lane, xa);
-    u_read_chunks<true>(st + 2 * U_TILE_BYTES, warp, lane, xb);
-    u_write_split<true>(st, st + U_TILE_BYTES, warp, lane, xa);
-    u_write_split<true>(st + 2 * U_TILE_BYTES, st + 3 * U_TILE_BYTES, warp, lane, xb);
+    const uint32_t KT = kbase + (uint32_t)kt, stage = KT % USTAGES;
+    u_mbar_wait(&bars.raw[stage], (KT / USTAGES) & 1u);
+    unsigned char* st = u_smem + stage * U_STAGE_BYTES;
+    // small = x - (x with the low 13 mantissa bits cleared), same layout as the raw tile: a linear pass
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4* raw = reinterpret_cast<const float4*>(st + h * 2 * U_TILE_BYTES);
+      float4* sml = reinterpret_cast<float4*>(st + h * 2 * U_TILE_BYTES + U_TILE_BYTES);
+      float4 x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = raw[tid + j * U_PRODUCERS];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 r;
+        r.x = x[j].x - __uint_as_float(__float_as_uint(x[j].x) & 0xffffe000u);
+        r.y = x[j].y - __uint_as_float(__float_as_uint(x[j].y) & 0xffffe000u);
+        r.z = x[j].z - __uint_as_float(__float_as_uint(x[j].z) & 0xffffe000u);
+        r.w = x[j].w - __uint_as_float(__float_as_uint(x[j].w) & 0xffffe000u);
+        sml[tid + j * U_PRODUCERS] = r;
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA unit
-    u_mbar_arrive(&bars.full[KT % USTAGES]);
+    u_mbar_arrive(&bars.full[stage]);
     if (kt % UGROUP >= 1 && drained < kt / UGROUP) { drain(drained); ++drained; }
   }
-  cp_async_wait<0>();
   while (drained < ngroups) { drain(drained); ++drained; }
 }
 
-// epilogue + store of the 64 columns a worker holds
-__device__ __forceinline__ void gemm_store(const TileParams& P, const GemmStage& g, const GemmItem& it,
-                                           const float (&sum)[64], int warp, int lane) {
-  const int m0 = it.tile * P.m_tile, m_end = m0 + tile_rows(P, it.tile);
-  const int row = m0 + 32 * (warp & 3) + lane;
-  if (row >= m_end) return;
-  const int nb = it.ntile * UN + (warp >> 2) * 64;
-  const bool vec = (g.n_split & 3) == 0 && (g.ldo & 3) == 0 && (g.n_total & 3) == 0;
+// Epilogue.  The accumulators first go through shared memory (the operand stages are idle by then) so that
+// every warp then handles whole ROWS: bias / mask reads and the output stores are coalesced 512-byte runs, and the
+// code is one short loop (an epilogue unrolled over the 64 columns a thread holds is > 100 KB of instructions and
+// thrashes the instruction cache).  Requires n_total, n_split and ldo to be multiples of 4.
+constexpr int kTilePitch = UN + 4;  // floats per row of the staged tile: conflict-free 128-bit writes and reads
+
+__device__ __forceinline__ void gemm_stage_tile(float* tile, const float (&sum)[64], int warp, int lane) {
+  float* dst = tile + (size_t)(32 * (warp & 3) + lane) * kTilePitch + (warp >> 2) * 64;
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int n = nb + 4 * c;
-    if (n >= g.n_total) break;
-    float r[4] = {sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int col = n + e;
-      if (col >= g.n_total) continue;
-      const bool hi = col >= g.n_split;
-      float v = r[e];
-      if (g.bias) v += hi ? g.bias2[col - g.n_split] : g.bias[col];
-      if (g.epi == kEpiRelu) v = fmaxf(v, 0.f);
-      else if (g.epi == kEpiSigmoid) v = sigmoidf_ref(v);
-      else if (g.epi == kEpiMask) v = __ldg(g.mask + (size_t)row * g.ldmask + col) > 0.f ? v : 0.f;
-      else v = v / g.div;
-      r[e] = v;
-    }
-    const bool hi = n >= g.n_split;
-    float* dst = (hi ? g.out2 + (size_t)row * g.ldo + (n - g.n_split) : g.out + (size_t)row * g.ldo + n);
-    if (vec) {
-      *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+  for (int c = 0; c < 16; ++c)
+    *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
+}
+
+__device__ __noinline__ void gemm_store_rows(const TileParams& P, const GemmStage& g, int tile_idx, int ntile,
+                                             const float* tile, int warp, int lane) {
+  const int m0 = tile_idx * P.m_tile, rows = tile_rows(P, tile_idx);
+  const int col = ntile * UN + 4 * lane;
+  if (col >= g.n_total) return;
+  const bool hi = col >= g.n_split;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g.bias) bias = __ldg(reinterpret_cast<const float4*>(hi ? g.bias2 + (col - g.n_split) : g.bias + col));
+  float* obase = hi ? g.out2 + (col - g.n_split) : g.out + col;
+  const int epi = g.epi;
+  const float div = g.div;
+  for (int r = warp; r < rows; r += U_PRODUCERS / 32) {
+    float4 v = *reinterpret_cast<const float4*>(tile + (size_t)r * kTilePitch + 4 * lane);
+    v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+    if (epi == kEpiRelu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    } else if (epi == kEpiSigmoid) {
+      v.x = sigmoidf_ref(v.x); v.y = sigmoidf_ref(v.y); v.z = sigmoidf_ref(v.z); v.w = sigmoidf_ref(v.w);
+    } else if (epi == kEpiMask) {
+      const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + (size_t)(m0 + r) * g.ldmask + col));
+      v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
     } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = n + e;
-        if (col >= g.n_total) continue;
-        if (col >= g.n_split) g.out2[(size_t)row * g.ldo + (col - g.n_split)] = r[e];
-        else g.out[(size_t)row * g.ldo + col] = r[e];
-      }
+      v.x = v.x / div; v.y = v.y / div; v.z = v.z / div; v.w = v.w / div;
     }
+    *reinterpret_cast<float4*>(obase + (size_t)(m0 + r) * g.ldo) = v;
   }
 }
 
@@ -591,14 +710,16 @@ __device__ void colsum_item(const ColItem& ci, int colblock, float* scratch, int
   __syncthreads();
 }
 
-__device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem, int tid) {
-  __shared__ __align__(8) uint64_t bar_full[USTAGES], bar_empty[USTAGES], bar_acc_full[2], bar_acc_empty[2];
+__device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem, int tid, long long* st_cycles) {
+  __shared__ __align__(8) uint64_t bar_raw[USTAGES], bar_full[USTAGES], bar_empty[USTAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t s_tmem;
   __shared__ unsigned s_ticket, s_flag;
   const int warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < USTAGES; ++s) { u_mbar_init(&bar_full[s], U_PRODUCERS); u_mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < USTAGES; ++s) {
+      u_mbar_init(&bar_raw[s], 1); u_mbar_init(&bar_full[s], U_PRODUCERS); u_mbar_init(&bar_empty[s], 1);
+    }
 #pragma unroll
     for (int b = 0; b < 2; ++b) { u_mbar_init(&bar_acc_full[b], 1); u_mbar_init(&bar_acc_empty[b], U_PRODUCERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -613,7 +734,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
-  const GemmBars bars{bar_full, bar_empty, bar_acc_full, bar_acc_empty};
+  const GemmBars bars{bar_raw, bar_full, bar_empty, bar_acc_full, bar_acc_empty};
 
   if (P.w_cat_t) {  // backward: K-major copies of the weights for the dH / dZ products
     if (warp < 8) transpose_weights(P, grank, reinterpret_cast<float*>(u_smem), warp, lane);
@@ -631,6 +752,8 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
   const unsigned total = per_tile * (unsigned)T + (unsigned)cs_blocks[4];
   uint32_t kbase = 0, gbase = 0;
   float sum[64];
+  long long c_dep = 0, c_main = 0, c_epi = 0, n_items = 0, c_e[4] = {0, 0, 0, 0};
+  const bool timing = st_cycles != nullptr && tid == 0;
 
   for (;;) {
     if (tid == 0) s_ticket = atomicAdd(&P.ctr[1], 1u);
@@ -641,7 +764,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
       // ---- column-sum item: needs every tile's R, F1 and F2 -----------------------------------------------------
       if (tid == 0) {
         for (int t = 0; t < T; ++t) {
-          const unsigned rneed = 16u * (unsigned)((size_t)tile_rows(P, t) * P.c / P.p);
+          const unsigned rneed = 2u * (unsigned)((size_t)tile_rows(P, t) * P.c / P.p);
           wait_counter(tile_ctr(P, t) + 0, rneed);
           wait_counter(tile_ctr(P, t) + 1, (unsigned)P.st[0].n_tiles);
           wait_counter(tile_ctr(P, t) + 2, (unsigned)P.st[1].n_tiles);
@@ -662,10 +785,11 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     it.ntile = rr / g.splits;
     it.split = rr - it.ntile * g.splits;
     unsigned* tc = tile_ctr(P, it.tile);
+    const long long tg0 = timing ? clk() : 0;
     if (tid == 0) {
       if (P.w_cat_t) wait_counter(&P.ctr[3], (unsigned)P.n_gemm);
       if (it.stage == 0) {
-        const unsigned rneed = 16u * (unsigned)((size_t)tile_rows(P, it.tile) * P.c / P.p);  // 2 mods x 8 warps
+        const unsigned rneed = 2u * (unsigned)((size_t)tile_rows(P, it.tile) * P.c / P.p);  // one per R item
         wait_counter(tc + 0, rneed);
         // the partial planes of this ring position were last used by tile - kRingTiles: fully folded?
         if (it.tile >= kRingTiles) wait_counter(tile_ctr(P, it.tile - kRingTiles) + 2, (unsigned)P.st[1].n_tiles);
@@ -677,7 +801,9 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     const int k_begin = it.split * g.k_per_split;
     const int k_end = min(g.k_total, k_begin + g.k_per_split);
     const int nk = k_end > k_begin ? (k_end - k_begin + UK - 1) / UK : 0;
-    gemm_item_mainloop(P, g, it, u_smem, bars, tmem, kbase, gbase, nk, sum, warp, lane);
+    const long long tg1 = timing ? clk() : 0;
+    gemm_item_mainloop(P, g, it, u_smem, bars, tmem, kbase, gbase, nk, sum, warp, lane, tid);
+    const long long tg2 = timing ? clk() : 0;
     kbase += (uint32_t)nk;
     gbase += (uint32_t)((nk + UGROUP - 1) / UGROUP);
 
@@ -714,12 +840,35 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
         }
       }
     }
+    const bool timing2 = st_cycles != nullptr && (tid == 128 || tid == 256);
+    const long long tg3 = (timing || timing2) ? clk() : 0;
+    long long tg4 = tg3, tg5 = tg3;
     if (finish) {
-      if (warp < 8) gemm_store(P, g, it, sum, warp, lane);
-      __threadfence();
+      if (warp < 8) gemm_stage_tile(reinterpret_cast<float*>(u_smem), sum, warp, lane);
       __syncthreads();
+      if (warp < 8) gemm_store_rows(P, g, it.tile, it.ntile, reinterpret_cast<const float*>(u_smem), warp, lane);
+      // the staged tile lives in the operand stages: order these generic accesses before the next item's TMA writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tg4 = (timing || timing2) ? clk() : 0;
+      __threadfence();
+      tg5 = (timing || timing2) ? clk() : 0;
+      __syncthreads();
+      if (timing2) {
+        const long long t6 = clk();
+        if (tid == 128) { st_cycles[12] += tg4 - tg3; st_cycles[13] += tg5 - tg4; }
+        else { st_cycles[14] += tg5 - tg4; st_cycles[15] += t6 - tg5; }
+      }
       if (tid == 0) red_release_add(tc + 1 + it.stage, 1u);
     }
+    if (timing) {
+      const long long tg6 = clk();
+      c_dep += tg1 - tg0; c_main += tg2 - tg1; c_epi += tg6 - tg2; ++n_items;
+      c_e[0] += tg3 - tg2; c_e[1] += tg4 - tg3; c_e[2] += tg5 - tg4; c_e[3] += tg6 - tg5;
+    }
+  }
+  if (timing) {
+    st_cycles[1] = n_items; st_cycles[2] = c_dep; st_cycles[3] = c_main; st_cycles[4] = c_epi;
+    st_cycles[8] = c_e[0]; st_cycles[9] = c_e[1]; st_cycles[10] = c_e[2]; st_cycles[11] = c_e[3];
   }
   // every warp is done with its tcgen05.ld before the columns go back to the allocator
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -739,27 +888,31 @@ __global__ void __launch_bounds__(kThreads, 1) tile_pipeline_kernel(const __grid
   if (tid == 0) s_role = atomicAdd(&P.ctr[2], 1u);
   __syncthreads();
   const int role = (int)s_role;
+  long long* st_cycles = P.stats ? P.stats + (size_t)blockIdx.x * 16 : nullptr;
+  const long long t_begin = st_cycles ? clk() : 0;
   if (role < P.n_gemm) {
-    gemm_role(P, role, smem, tid);
+    gemm_role(P, role, smem, tid, st_cycles);
+    if (st_cycles && tid == 0) { st_cycles[0] = 1; st_cycles[7] = clk() - t_begin; }
     return;
   }
   if (tid == 0) {
-    for (int s = 0; s < P.slots; ++s) { u_mbar_init(&s_full[s], 1); u_mbar_init(&s_empty[s], U_PRODUCERS / 32); }
+    for (int s = 0; s < P.slots; ++s) { u_mbar_init(&s_full[s], 1); u_mbar_init(&s_empty[s], P.wps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   StreamSmem sm{smem, P.slot_bytes, P.chunk_bytes, P.p};
   if (tid >= U_PRODUCERS) {
-    if (tid == U_PRODUCERS) stream_loader(P, sm, s_meta, s_full, s_empty);
+    if (tid == U_PRODUCERS) stream_loader(P, sm, s_meta, s_full, s_empty, st_cycles);
     __syncwarp();
   } else {
-    stream_workers(P, sm, s_meta, s_full, s_empty, tid);
+    stream_workers(P, sm, s_meta, s_full, s_empty, tid, st_cycles);
+    if (st_cycles && tid == 0) { st_cycles[0] = 0; st_cycles[7] = clk() - t_begin; }
   }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
 struct TileCfg {
-  int m_tile, n_tiles, p, lanes, n_gemm, slots, nbuf, lag;
+  int m_tile, n_tiles, p, lanes, lanes_log2, n_gemm, slots, wps, nbuf, lag;
   uint32_t chunk_bytes, slot_bytes;
   int nt[2], splits[2], kps[2];
   size_t part_tile_floats, ctr_bytes, part_bytes, smem_bytes;
@@ -791,17 +944,28 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   }
   if (!f.p) return false;
   f.chunk_bytes = (uint32_t)((size_t)f.p * hw * 4);
-  int lanes = 1;
-  while (lanes < 32 && lanes * 2 * f.p <= U_PRODUCERS) lanes *= 2;
+  // lanes per plane inside a worker warp: 128-bit walks want >= 8 lanes on a plane (a quarter warp then reads 128
+  // contiguous bytes: conflict-free) and a few vectors per lane; scalar walks (HW % 4 != 0) of short planes use one
+  // lane per plane (an odd HW makes the 32 planes of a warp hit 32 different banks) and need no shuffles
+  int lanes = 1, lg = 0;
+  if (hw % 4 == 0) {
+    const int hw4 = hw / 4;
+    while (lanes < 32 && lanes * 6 <= hw4) { lanes *= 2; ++lg; }
+    if (lanes < 8 && hw4 >= 8) { lanes = 8; lg = 3; }
+  } else {
+    while (lanes < 32 && lanes * 64 < hw) { lanes *= 2; ++lg; }
+  }
   f.lanes = lanes;
+  f.lanes_log2 = lg;
   f.nbuf = bwd ? 2 : 1;
   f.slot_bytes = (uint32_t)round_up((size_t)f.nbuf * f.chunk_bytes + 2 * (size_t)f.p * 4, 128);
   const size_t gemm_smem = (size_t)USTAGES * U_STAGE_BYTES;
   const size_t budget = 224 * 1024 - 1024;
   int slots = (int)(budget / f.slot_bytes);
-  if (slots > kMaxSlots) slots = kMaxSlots;
   if (slots < 2) return false;
+  slots = slots >= 8 ? 8 : (slots >= 4 ? 4 : 2);  // a power of two: 8 / slots worker warps serve one slot
   f.slots = slots;
+  f.wps = (U_PRODUCERS / 32) / slots;
   size_t sm = (size_t)slots * f.slot_bytes;
   if (sm < gemm_smem) sm = gemm_smem;
   f.smem_bytes = sm + 1024;
@@ -846,21 +1010,53 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   return true;
 }
 
+// ---- TMA tensor maps (driver entry point resolved at run time: no link-time dependency on libcuda) ---------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// fp32 [rows, k] with leading dimension ld (elements): box 32 k x 32 rows, 128-byte swizzle, zeros out of range
+int make_map(CUtensorMap* m, const float* base, int rows, int k, int ld) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return GML_E_UNSUPPORTED;
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)UK, 32u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GML_OK : GML_E_UNSUPPORTED;
+}
+
 void fill_common(TileParams& P, const TileCfg& f, int n, int c, int hw, int d, bool bwd, void* ws) {
   P.n = n; P.c = c; P.hw = hw; P.d = d; P.bwd = bwd ? 1 : 0;
-  P.m_tile = f.m_tile; P.n_tiles = f.n_tiles; P.p = f.p; P.lanes = f.lanes; P.lag = f.lag; P.n_gemm = f.n_gemm;
-  P.slots = f.slots; P.nbuf = f.nbuf; P.chunk_bytes = f.chunk_bytes; P.slot_bytes = f.slot_bytes;
+  P.m_tile = f.m_tile; P.n_tiles = f.n_tiles; P.p = f.p; P.lanes = f.lanes; P.lanes_log2 = f.lanes_log2; P.lag = f.lag;
+  P.n_gemm = f.n_gemm; P.slots = f.slots; P.wps = f.wps; P.nbuf = f.nbuf; P.chunk_bytes = f.chunk_bytes; P.slot_bytes = f.slot_bytes;
   P.hw_magic = (uint32_t)(((1ull << 32) + (unsigned)hw - 1) / (unsigned)hw);
   P.ctr = reinterpret_cast<unsigned*>(ws);
   P.part = reinterpret_cast<float*>(static_cast<char*>(ws) + f.ctr_bytes);
   P.part_tile_floats = f.part_tile_floats;
   for (int s = 0; s < 2; ++s) {
     P.st[s].n_tiles = f.nt[s]; P.st[s].splits = f.splits[s]; P.st[s].k_per_split = f.kps[s];
-    P.st[s].a2 = nullptr; P.st[s].lda2 = 0; P.st[s].k_split = 0; P.st[s].b2 = nullptr;
+    P.st[s].k_split = 0;
     P.st[s].out2 = nullptr; P.st[s].bias = nullptr; P.st[s].bias2 = nullptr; P.st[s].mask = nullptr; P.st[s].ldmask = 0;
     P.st[s].div = 1.f;
   }
   P.n_cs = 0;
+  P.stats = g_tile_stats;
   P.w_cat_t = nullptr; P.w_sq_t = nullptr; P.w_v = P.w_s = P.w_sq = nullptr;
 }
 
@@ -922,7 +1118,7 @@ int launch_tile_fwd(const FusedFwdArgs& a, float* gate_sum, float* run_v, float*
   TileCfg f;
   if (!make_tile_cfg(a.n, a.c, a.hw, a.d, false, &f)) return GML_E_UNSUPPORTED;
   if (!ws || ws_bytes < f.ctr_bytes + f.part_bytes) return GML_E_WORKSPACE;
-  const void* al[] = {a.a, a.b, a.a_out, a.b_out, a.w_sq, a.w_v, a.w_s, a.z, a.h, a.g_a, a.g_b, ws};
+  const void* al[] = {a.a, a.b, a.a_out, a.b_out, a.w_sq, a.w_v, a.w_s, a.b_sq, a.b_v, a.b_s, a.z, a.h, a.g_a, a.g_b, ws};
   for (const void* p : al)
     if (!aligned16(p)) return GML_E_UNSUPPORTED;
   TileParams P;
@@ -934,10 +1130,17 @@ int launch_tile_fwd(const FusedFwdArgs& a, float* gate_sum, float* run_v, float*
   P.rout[0] = a.z; P.rout[1] = a.z + a.c; P.rout_ld = 2 * a.c;
   P.gate_scale = a.gate_scale;
   GemmStage& s0 = P.st[0];   // H = relu(Z Wsq^T + bsq)
-  s0.a = a.z; s0.lda = 2 * a.c; s0.b = a.w_sq; s0.ldb = 2 * a.c; s0.n_split = a.d; s0.n_total = a.d; s0.k_total = 2 * a.c;
+  GML_TRY(make_map(&s0.tm_a, a.z, a.n, 2 * a.c, 2 * a.c));
+  GML_TRY(make_map(&s0.tm_b, a.w_sq, a.d, 2 * a.c, 2 * a.c));
+  s0.tm_a2 = s0.tm_a; s0.tm_b2 = s0.tm_b;
+  s0.n_split = a.d; s0.n_total = a.d; s0.k_total = 2 * a.c;
   s0.out = a.h; s0.ldo = a.d; s0.bias = a.b_sq; s0.epi = kEpiRelu;
   GemmStage& s1 = P.st[1];   // [g_a | g_b] = sigmoid(H [Wv ; Ws]^T + [bv | bs])
-  s1.a = a.h; s1.lda = a.d; s1.b = a.w_v; s1.b2 = a.w_s; s1.ldb = a.d; s1.n_split = a.c; s1.n_total = 2 * a.c;
+  GML_TRY(make_map(&s1.tm_a, a.h, a.n, a.d, a.d));
+  GML_TRY(make_map(&s1.tm_b, a.w_v, a.c, a.d, a.d));
+  GML_TRY(make_map(&s1.tm_b2, a.w_s, a.c, a.d, a.d));
+  s1.tm_a2 = s1.tm_a;
+  s1.n_split = a.c; s1.n_total = 2 * a.c;
   s1.k_total = a.d; s1.out = a.g_a; s1.out2 = a.g_b; s1.ldo = a.c; s1.bias = a.b_v; s1.bias2 = a.b_s; s1.epi = kEpiSigmoid;
   if (gate_sum) {
     P.cs[0] = ColItem{a.g_a, gate_sum, a.n, a.c, a.c, run_v, run_s, (float)a.n, step};
@@ -971,13 +1174,19 @@ int launch_tile_bwd(const FusedBwdArgs& a, float* dz_flat, float* d_b_v, float* 
   P.rout[0] = a.de_a; P.rout[1] = a.de_b; P.rout_ld = a.c;
   P.gate_scale = a.gate_scale;
   GemmStage& s0 = P.st[0];   // dH = ([dE_a | dE_b] [Wv ; Ws]) * [H > 0]
-  s0.a = a.de_a; s0.a2 = a.de_b; s0.lda = a.c; s0.lda2 = a.c; s0.k_split = a.c;
-  s0.b = P.w_cat_t; s0.ldb = 2 * a.c; s0.n_split = a.d; s0.n_total = a.d; s0.k_total = 2 * a.c;
+  GML_TRY(make_map(&s0.tm_a, a.de_a, a.n, a.c, a.c));
+  GML_TRY(make_map(&s0.tm_a2, a.de_b, a.n, a.c, a.c));
+  GML_TRY(make_map(&s0.tm_b, P.w_cat_t, a.d, 2 * a.c, 2 * a.c));
+  s0.tm_b2 = s0.tm_b;
+  s0.k_split = a.c; s0.n_split = a.d; s0.n_total = a.d; s0.k_total = 2 * a.c;
   s0.out = a.dh; s0.ldo = a.d; s0.mask = a.h; s0.ldmask = a.d; s0.epi = kEpiMask;
   GemmStage& s1 = P.st[1];   // dZ = dH Wsq, stored per modality and already divided by HW (MeanBackward)
-  // (w_sq_t is ONE [2C, D] matrix: b2 simply continues it at row C, where the output switches to dz_b)
-  s1.a = a.dh; s1.lda = a.d; s1.b = P.w_sq_t; s1.b2 = P.w_sq_t + (size_t)a.c * a.d; s1.ldb = a.d; s1.n_split = a.c;
-  s1.n_total = 2 * a.c; s1.k_total = a.d; s1.out = dz_a; s1.out2 = dz_b; s1.ldo = a.c; s1.epi = kEpiDiv;
+  // (w_sq_t is ONE [2C, D] matrix: the second map simply continues it at row C, where the output switches to dz_b)
+  GML_TRY(make_map(&s1.tm_a, a.dh, a.n, a.d, a.d));
+  GML_TRY(make_map(&s1.tm_b, P.w_sq_t, a.c, a.d, a.d));
+  GML_TRY(make_map(&s1.tm_b2, P.w_sq_t + (size_t)a.c * a.d, a.c, a.d, a.d));
+  s1.tm_a2 = s1.tm_a;
+  s1.n_split = a.c; s1.n_total = 2 * a.c; s1.k_total = a.d; s1.out = dz_a; s1.out2 = dz_b; s1.ldo = a.c; s1.epi = kEpiDiv;
   s1.div = (float)a.hw;
   int ncs = 0;
   if (d_b_v) P.cs[ncs++] = ColItem{a.de_a, d_b_v, a.n, a.c, a.c, nullptr, nullptr, 1.f, 0.f};

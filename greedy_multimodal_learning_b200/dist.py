@@ -72,17 +72,41 @@ def shard_batch(n_global: int, rank_: Optional[int] = None, world: Optional[int]
 
 class ShardedBatches:
     """Wrap a loader of GLOBAL batches `(idx, data, label)`; yield this rank's shard of each.
-    Keeps the reference's tuple layout (dataset.py:116-128)."""
+    Keeps the reference's tuple layout (dataset.py:116-128).
 
-    def __init__(self, loader, rank_=None, world=None):
-        self.loader, self.rank, self.world = loader, rank_, world
+    Every rank gets the SAME number of samples: a global batch whose size is not a multiple of the world size
+    loses its last `len % world` samples (remainder="drop", default) or repeats its first samples to fill up
+    (remainder="pad").  Equal shards are what makes the mean of the per-rank mean-loss gradients
+    (GradientAllReduce: sum / world) equal the global-batch mean gradient, and no rank ever sees an empty shard
+    (an empty shard would skip the gate-sum all-reduce the other ranks are waiting in).  Batches smaller than the
+    world size are skipped on every rank under "drop"."""
+
+    def __init__(self, loader, rank_=None, world=None, remainder="drop"):
+        if remainder not in ("drop", "pad"):
+            raise ValueError("remainder must be 'drop' or 'pad'")
+        self.loader, self.rank, self.world, self.remainder = loader, rank_, world, remainder
 
     def __len__(self):
         return len(self.loader)
 
     def __iter__(self):
+        world = world_size() if self.world is None else self.world
         for idx, data, label in self.loader:
-            lo, hi = shard_batch(len(label), self.rank, self.world)
+            n = len(label)
+            if n % world:
+                if self.remainder == "drop":
+                    n -= n % world
+                    if n == 0:
+                        continue
+                    idx, data, label = idx[:n], data[:n], label[:n]
+                else:
+                    extra = world - n % world
+                    rep = [i % n for i in range(extra)]
+                    idx = torch.cat([torch.as_tensor(idx), torch.as_tensor(idx)[rep]])
+                    data = torch.cat([torch.as_tensor(data), torch.as_tensor(data)[rep]])
+                    label = torch.cat([torch.as_tensor(label), torch.as_tensor(label)[rep]])
+                    n += extra
+            lo, hi = shard_batch(n, self.rank, world)
             yield idx[lo:hi], data[lo:hi], label[lo:hi]
 
 
@@ -95,6 +119,12 @@ class GradientAllReduce:
     semantics are enforced by `zero_grad`).  A post-accumulate-grad hook counts arrivals; the
     bucket's all-reduce is issued on the communication stream when it is complete.
     `finish()` waits for all buckets and scales by 1/world.
+
+    Parameters that received NO gradient in a step (the substituted side's excitation FC inside a curation window,
+    reference src/balanced_mmtm.py:135-152) get `.grad = None` for the optimizer step, exactly like the single-GPU
+    path under `optimizer.zero_grad()` (set_to_none=True): SGD with momentum / weight decay must skip them rather
+    than step them with a zero gradient.  `zero_grad()` re-attaches their bucket views.  (Every rank runs the same
+    mode, so the set is rank-identical and the all-reduce of the zero slice is harmless.)
     """
 
     def __init__(self, model: torch.nn.Module, bucket_mb: float = 32.0, group=None, average: bool = True):
@@ -127,6 +157,8 @@ class GradientAllReduce:
                 off += p.numel()
             self.buckets.append(flat)
         self._sizes = [len(g) for g in groups]
+        self._views = {p: p.grad for p in params}
+        self._fired = set()
         self._arrived = [0] * len(groups)
         self._works = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
@@ -134,11 +166,16 @@ class GradientAllReduce:
 
     def zero_grad(self):
         """Zero the flat buckets in place (keeps .grad views; one memset per bucket)."""
+        for p in self.params:
+            if p.grad is not self._views[p]:
+                p.grad = self._views[p]
         for flat in self.buckets:
             flat.zero_()
         self._arrived = [0] * len(self.buckets)
+        self._fired = set()
 
     def _on_grad(self, p):
+        self._fired.add(p)
         b = self._bucket_of[p]
         self._arrived[b] += 1
         if self._arrived[b] == self._sizes[b]:
@@ -172,6 +209,10 @@ class GradientAllReduce:
                 flat.div_(self.world)
         self._works = []
         self._arrived = [0] * len(self.buckets)
+        if len(self._fired) != len(self.params):
+            for p in self.params:
+                if p not in self._fired:
+                    p.grad = None  # no gradient this step: the optimizer skips it (single-GPU semantics)
 
     def remove(self):
         for h in self._hooks:

@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE -- not product code.  Used by `tests/golden/make_golden.py` to
 generate the committed golden vectors and by the (skippable) tests that pin the
 oracle restatement against the real reference.  `/root/reference` does not exist on
-the GPU box, so nothing that runs there may depend on this module succeeding:
+the GPU box; `__graft_entry__.build()` mirrors the unmodified tree into the git-ignored
+`baseline/_ref/`, which travels with the snapshot.  Nothing may depend on either being there:
 `reference_available()` is the guard.
 
 The reference needs three packages that are not installed in this image
@@ -19,7 +20,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("GML_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _default_root():
+    """The reference tree where it lies (authoring container), else the git-ignored mirror `baseline/_ref`
+    that `__graft_entry__.build()` makes of it (unmodified files; it travels to the GPU box with the snapshot)."""
+    for cand in (os.environ.get("GML_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "src", "balanced_mmtm.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available() -> bool:

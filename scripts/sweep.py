@@ -21,6 +21,24 @@ from greedy_multimodal_learning_b200 import _lib as L  # noqa: E402
 VARIANTS = {
     # name: (flags, tunables)
     "auto": (0, {}),
+    "old": (0, {"tile_kind": 2}),
+    "tile": (L.F_FORCE_TILE, {}),
+    "tile_lag1": (L.F_FORCE_TILE, {"tile_lag": 1}),
+    "tile_lag3": (L.F_FORCE_TILE, {"tile_lag": 3}),
+    "tile_lag4": (L.F_FORCE_TILE, {"tile_lag": 4}),
+    "tile_m16": (L.F_FORCE_TILE, {"tile_m": 16}),
+    "tile_m32": (L.F_FORCE_TILE, {"tile_m": 32}),
+    "tile_m64": (L.F_FORCE_TILE, {"tile_m": 64}),
+    "tile_m128": (L.F_FORCE_TILE, {"tile_m": 128}),
+    "tile_g4": (L.F_FORCE_TILE, {"tile_gemm_ctas": 4}),
+    "tile_g8": (L.F_FORCE_TILE, {"tile_gemm_ctas": 8}),
+    "tile_g12": (L.F_FORCE_TILE, {"tile_gemm_ctas": 12}),
+    "tile_g16": (L.F_FORCE_TILE, {"tile_gemm_ctas": 16}),
+    "tile_g24": (L.F_FORCE_TILE, {"tile_gemm_ctas": 24}),
+    "tile_g32": (L.F_FORCE_TILE, {"tile_gemm_ctas": 32}),
+    "tile_g40": (L.F_FORCE_TILE, {"tile_gemm_ctas": 40}),
+    "tile_c14": (L.F_FORCE_TILE, {"tile_chunk_kb": 14}),
+    "tile_c50": (L.F_FORCE_TILE, {"tile_chunk_kb": 50}),
     "auto_biggemm": (0, {"gemm_big_tiles": 1}),
     "auto_ffma": (0, {"gemm_tf32x3": 0, "gemm_umma": 0}),
     "auto_mmasync": (0, {"gemm_umma": 0}),
@@ -90,7 +108,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 2, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 rc = fwd(flags)
                 if rc == -5:

@@ -98,7 +98,10 @@ def _grad_worker(rank, world):
     h = model[0](x[lo:hi]).relu()
     h.sum().backward()
     red.finish()  # must not hang although most hooks never fired
-    assert float(model[4].weight.grad.abs().sum()) == 0.0
+    # no gradient this step -> .grad is None for the optimizer (single-GPU zero_grad(set_to_none=True) semantics)
+    assert model[4].weight.grad is None and model[2].weight.grad is None and model[0].weight.grad is not None
+    opt.zero_grad()
+    assert model[4].weight.grad is not None and float(model[4].weight.grad.abs().sum()) == 0.0  # view re-attached
     return [[g.numpy() for g in grads] for grads in out], [p.detach().numpy() for p in model.parameters()]
 
 
@@ -117,6 +120,61 @@ def test_gradient_allreduce_matches_single_process_full_batch():
         opt.step()
     for a, b in zip(res[0][1], res[1][1]):  # replicas stay identical
         assert np.array_equal(a, b)
+
+
+def _window_worker(rank, world):
+    """Momentum + weight decay across steps in which the last layer gets NO gradient (what a curation window does to
+    the substituted side's excitation FC): data-parallel weights must follow the single-process run."""
+    x, y = _data()
+    model = _tiny_model()
+    gdist.broadcast_parameters(model)
+    red = gdist.GradientAllReduce(model, bucket_mb=0.0005)
+    opt = gdist.DPOptimizer(torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=0.01), red)
+    lo, hi = gdist.shard_batch(len(y))
+    for step in range(6):
+        opt.zero_grad()
+        if step in (2, 3):   # "window": the head is bypassed
+            loss = model[2](model[1](model[0](x[lo:hi]))).pow(2).mean()
+        else:
+            loss = torch.nn.functional.cross_entropy(model(x[lo:hi]), y[lo:hi])
+        loss.backward()
+        red.finish()
+        opt.step()
+    return [p.detach().numpy() for p in model.parameters()]
+
+
+def test_data_parallel_matches_single_process_across_a_no_gradient_window():
+    res = _spawn(_window_worker)
+    x, y = _data()
+    model = _tiny_model()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=0.01)
+    for step in range(6):
+        opt.zero_grad()  # set_to_none=True: the head's .grad is None inside the window -> SGD skips it
+        if step in (2, 3):
+            loss = model[2](model[1](model[0](x))).pow(2).mean()
+        else:
+            loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss.backward()
+        opt.step()
+    for rank in range(2):
+        for got, p in zip(res[rank], model.parameters()):
+            np.testing.assert_allclose(got, p.detach().numpy(), rtol=2e-5, atol=1e-6)
+
+
+def test_sharded_batches_remainder_policy():
+    mk = lambda n: [(torch.arange(n), torch.arange(n * 2).view(n, 2).float(), torch.arange(n) % 3)]
+    # 7 samples on 2 ranks: drop the last one -> 3 + 3, identical sizes, no empty shard
+    a = list(gdist.ShardedBatches(mk(7), 0, 2))[0]
+    b = list(gdist.ShardedBatches(mk(7), 1, 2))[0]
+    assert len(a[2]) == len(b[2]) == 3 and torch.equal(torch.cat([a[0], b[0]]), torch.arange(6))
+    # fewer samples than ranks: the batch is skipped on every rank
+    assert list(gdist.ShardedBatches(mk(1), 0, 2)) == [] and list(gdist.ShardedBatches(mk(1), 1, 2)) == []
+    # pad: 7 -> 8 by repeating the first sample
+    a = list(gdist.ShardedBatches(mk(7), 0, 2, remainder="pad"))[0]
+    b = list(gdist.ShardedBatches(mk(7), 1, 2, remainder="pad"))[0]
+    assert len(a[2]) == len(b[2]) == 4 and int(b[0][-1]) == 0
+    with pytest.raises(ValueError):
+        gdist.ShardedBatches(mk(4), 0, 2, remainder="keep")
 
 
 def test_shard_batch_partitions_exactly():
