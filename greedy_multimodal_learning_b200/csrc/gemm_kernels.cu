@@ -510,30 +510,22 @@ __global__ void __launch_bounds__(UTHREADS, 1) gemm_umma_kernel(const PipeBatch 
   for (int i = 0; i < 64; ++i) sum[i] = 0.f;
 
   if (warp == U_PRODUCERS / 32) {
-    // ===== MMA issuer =====================================================================
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp converged, one lane elected inside each instruction (umma.cuh) ==========
+    {
       // instruction descriptor: D fp32 [4,6)=1, A and B TF32 [7,10)=[10,13)=2, both K-major, N >> 3 at [17,23),
       // M >> 4 at [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-      for (int kt = 0; kt < nk; ++kt) {
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, u_smem_addr(u_smem), 0);
+      const uint32_t utmem = __shfl_sync(0xffffffffu, tmem, 0);
+      const int unk = __shfl_sync(0xffffffffu, nk, 0);
+      for (int kt = 0; kt < unk; ++kt) {
         const int stage = kt % USTAGES, g = kt / UGROUP, b = g & 1;
         if (kt % UGROUP == 0 && g >= 2) u_mbar_wait(&bar_acc_empty[b], (uint32_t)(((g >> 1) - 1) & 1));
         u_mbar_wait(&bar_full[stage], (uint32_t)((kt / USTAGES) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_big = u_smem_addr(u_smem + stage * U_STAGE_BYTES), a_small = a_big + U_TILE_BYTES;
-        const uint32_t b_big = a_big + 2 * U_TILE_BYTES, b_small = a_big + 3 * U_TILE_BYTES;
-        const uint32_t acc = tmem + (uint32_t)(b * UN);
-#pragma unroll
-        for (int j = 0; j < UK / 8; ++j) {
-          const uint32_t o = (uint32_t)j * 32u;  // 8 k further inside the 128-byte rows
-          const uint64_t da_b = u_desc(a_big + o), da_s = u_desc(a_small + o);
-          const uint64_t db_b = u_desc(b_big + o), db_s = u_desc(b_small + o);
-          u_mma_tf32(acc, da_s, db_b, idesc, (kt % UGROUP != 0 || j != 0) ? 1u : 0u);
-          u_mma_tf32(acc, da_b, db_s, idesc, 1u);
-          u_mma_tf32(acc, da_b, db_b, idesc, 1u);
-        }
-        u_commit(&bar_empty[stage]);
-        if (kt % UGROUP == UGROUP - 1 || kt == nk - 1) u_commit(&bar_acc_full[b]);
+        u_mma_stage_elect(smem_base, (uint32_t)(stage * U_STAGE_BYTES), utmem + (uint32_t)(b * UN), kt % UGROUP == 0, idesc);
+        u_commit_elect(&bar_empty[stage]);
+        if (kt % UGROUP == UGROUP - 1 || kt == unk - 1) u_commit_elect(&bar_acc_full[b]);
       }
     }
     __syncwarp();

@@ -45,6 +45,7 @@ int g_tile_gemm_ctas = 0;   // tunable "tile_gemm_ctas": 0 = from the FLOP/byte 
 int g_tile_m = 0;           // tunable "tile_m": samples per tile, 0 = automatic (~25 MB of feature map per tile)
 int g_tile_chunk_kb = 28;   // tunable "tile_chunk_kb": upper bound of a chunk (one work item) in KB
 int g_tile_min_mb = 8;      // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality
+int g_tile_nodeps = 0;      // debug/measurement ONLY (wrong results): S items do not wait for the gates
 long long* g_tile_stats = nullptr;  // debug: per-CTA cycle breakdown (device buffer, 16 slots per CTA)
 
 namespace {
@@ -98,12 +99,16 @@ struct TileParams {
   float* w_cat_t; float* w_sq_t;   // [D, 2C], [2C, D]; nullptr in the forward
   int n, c, hw, d, bwd;
   int m_tile, n_tiles, p, lanes, lanes_log2, lag, n_gemm;
-  int slots, wps, nbuf;      // slots is a power of two <= 8; wps = 8 / slots worker warps serve one slot
+  int slots_log2, cps;       // log2(slots); chunks per (sample, modality) = C / P
+  uint32_t cps_magic;        // ceil(2^32 / cps): ch / cps == __umulhi(ch, cps_magic) for ch < 2^16
+  int slots, wps, nbuf;      // slots = 2 * groups; a group of wps = 8 / groups worker warps owns two slots (one being
+                             // processed while the other one loads)
   uint32_t chunk_bytes, slot_bytes, hw_magic;
   float gate_scale;
   unsigned* ctr;
   float* part;
   size_t part_tile_floats;   // partial planes of one tile: (sum over stages of n_tiles * splits) * 128 * 128
+  int nodeps;                // measurement only: S items skip their dependency wait (results are garbage)
   long long* stats;          // debug (tunable "tile_stats_ptr"): 16 clock64 sums per CTA, or nullptr
 };
 
@@ -163,7 +168,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // 
   return ok != 0;
 }
 
-struct SlotMeta { int kind, mod, tile, q0, rofs, pad0, pad1, pad2; };  // rofs: offset of the chunk's first R result
+struct __align__(16) SlotMeta { int kind, mod, tile, q0, rofs, pad0, pad1, pad2; };  // rofs: offset of the chunk's first R result
 
 __device__ __forceinline__ int tile_rows(const TileParams& P, int t) {
   const int r = P.n - t * P.m_tile;
@@ -188,205 +193,283 @@ struct StreamSmem {
   __device__ __forceinline__ float* add(int slot, int nbuf) const { return gate(slot, nbuf) + p; }
 };
 
-// The loader also signals R-stage completion: a slot's `empty` barrier tells it that all eight worker warps are done
-// with the item that occupied the slot, so it can add this CTA's finished R items of a tile to the tile's global
-// counter with ONE release per (CTA, tile) instead of a gpu-scope fence per warp and item.
+// (all 32 lanes of a converged warp call these; one elected lane issues -- see umma.cuh for why)
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t}"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_el(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+
+// The loader: the WHOLE control warp runs it converged (every value below is the same in all lanes); instructions with
+// side effects are issued by one lane.  It has to sustain one ~25 KB item per few hundred cycles, so per item there is
+// no integer division (segment data is recomputed only when the ticket crosses into a new segment; sample / channel of
+// a chunk by multiplication), the S dependency is polled once per tile, and the TMA operands never sit in a divergent
+// region.
+// The loader also signals R-stage completion: a slot's `empty` barrier tells it that all worker warps of the slot are
+// done with the item that occupied it, so it adds this CTA's finished R items of a tile to the tile's global counter
+// with ONE release per (CTA, tile) instead of a gpu-scope fence per warp and item.
 __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMeta* metas, uint64_t* full, uint64_t* empty,
-                              long long* st_cycles) {
+                              long long* st_cycles, int lane) {
   const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
   const int T = P.n_tiles, nseg = 2 * (T + P.lag);
-  const size_t planes_per_tile = (size_t)P.m_tile * P.c;
-  int seg = 0;
-  unsigned seg_start = 0;
-  auto seg_tile = [&](int j) { return (j & 1) ? (j >> 1) - P.lag : (j >> 1); };
-  auto seg_size = [&](int j) -> unsigned {
-    const int t = seg_tile(j);
-    if (t < 0 || t >= T) return 0u;
-    return 2u * (unsigned)((size_t)tile_rows(P, t) * P.c / P.p);
+  const uint32_t smem0 = u_smem_addr(sm.base), full0 = u_smem_addr(full);
+  const uint32_t vec_bytes = (uint32_t)P.p * 4u;
+  // current segment (R or S stage of one tile): [seg_start, seg_end) in ticket space
+  int seg = -1, seg_t = 0, seg_kind = kItemR;
+  unsigned seg_start = 0, seg_end = 0, seg_chunks = 0;
+  int seg_qbase = 0, seg_n0 = 0;
+  auto next_segment = [&]() {
+    ++seg;
+    seg_start = seg_end;
+    if (seg >= nseg) { seg_end = 0xffffffffu; return; }
+    seg_kind = (seg & 1) ? kItemS : kItemR;
+    seg_t = (seg & 1) ? (seg >> 1) - P.lag : (seg >> 1);
+    if (seg_t < 0 || seg_t >= T) { seg_chunks = 0; return; }
+    seg_chunks = (unsigned)(tile_rows(P, seg_t) * P.cps);
+    seg_end = seg_start + 2u * seg_chunks;
+    seg_n0 = seg_t * P.m_tile;
+    seg_qbase = seg_n0 * P.c;
   };
+  next_segment();
   unsigned uses = 0;       // items issued so far; item u lives in slot u % slots
-  unsigned retired = 0;    // items [0, retired) are known to be finished by all worker warps
+  unsigned retired = 0;    // items [0, retired) are known to be finished by their worker warps
   int slot = 0;
   const unsigned need_f2 = (unsigned)P.st[1].n_tiles;
-  // R bookkeeping, indexed by tile & 15 (at most `slots` <= 8 different tiles can be in flight)
-  int rec_tile[kMaxSlots];               // tile of the R item in a slot, -1 for S
-  unsigned short issued[16], done[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { issued[i] = 0; done[i] = 0; }
-#pragma unroll
-  for (int i = 0; i < kMaxSlots; ++i) rec_tile[i] = -1;
-  int flush_tile = 0;                    // lowest tile whose R count this CTA has not published yet
+  int ready_tile = -1;     // highest tile whose gates are known to be complete
+  // R bookkeeping, all in registers (every lane holds the same values).  `iss` / `fin` pack four 16-bit counters: R items
+  // issued / finished for tiles flush_tile .. flush_tile + 3 (`flush_tile` = lowest tile whose count this CTA has not
+  // published yet); `rec` packs one byte per slot: 0x80 | (tile & 0x7f) for an R item, 0 for an S item.
+  unsigned long long iss = 0, fin = 0, rec = 0;
+  int flush_tile = 0;
   long long c_empty = 0, c_dep = 0;
+  const bool timing = st_cycles != nullptr;
 
+  auto account = [&](int s_) {   // the item in slot s_ is finished
+    const unsigned r = (unsigned)(rec >> (8 * s_)) & 0xffu;
+    if (r & 0x80u) {
+      const unsigned j = ((r & 0x7fu) - ((unsigned)flush_tile & 0x7fu)) & 0x7fu;  // tile - flush_tile (< 4 by construction)
+      fin += 1ull << (16 * j);
+    }
+  };
   // items [retired, upto) -> wait for their workers, account finished R items
   auto retire = [&](unsigned upto) {
     while (retired < upto) {
-      const int s_ = (int)(retired % (unsigned)P.slots);
-      u_mbar_wait(&empty[s_], (retired / (unsigned)P.slots) & 1u);
-      if (rec_tile[s_] >= 0) done[rec_tile[s_] & 15]++;
+      const int s_ = (int)(retired & (unsigned)(P.slots - 1));
+      u_mbar_wait(&empty[s_], (retired >> P.slots_log2) & 1u);
+      account(s_);
       ++retired;
     }
   };
   // the same without blocking: whatever the workers have finished by now
   auto retire_ready = [&]() {
     while (retired < uses) {
-      const int s_ = (int)(retired % (unsigned)P.slots);
-      if (!mbar_test(&empty[s_], (retired / (unsigned)P.slots) & 1u)) break;
-      if (rec_tile[s_] >= 0) done[rec_tile[s_] & 15]++;
+      const int s_ = (int)(retired & (unsigned)(P.slots - 1));
+      if (!mbar_test(&empty[s_], (retired >> P.slots_log2) & 1u)) break;
+      account(s_);
       ++retired;
     }
   };
   // publish every tile whose R items (of this CTA) are all issued and finished
   auto flush = [&](bool exhausted) {
-    while (flush_tile < T && (exhausted || seg > 2 * flush_tile) && done[flush_tile & 15] == issued[flush_tile & 15]) {
-      if (issued[flush_tile & 15]) red_release_add(tile_ctr(P, flush_tile) + 0, (unsigned)issued[flush_tile & 15]);
-      issued[flush_tile & 15] = 0; done[flush_tile & 15] = 0;
+    while (flush_tile < T && (exhausted || seg > 2 * flush_tile) && (fin & 0xffffull) == (iss & 0xffffull)) {
+      const unsigned cnt = (unsigned)(iss & 0xffffull);
+      if (cnt && lane == 0) red_release_add(tile_ctr(P, flush_tile) + 0, cnt);
+      iss >>= 16; fin >>= 16;
       ++flush_tile;
     }
+    __syncwarp();
   };
 
-  // tickets are drawn two at a time and one draw ahead: the atomic's round trip overlaps the current items
-  unsigned cur = atomicAdd(&P.ctr[0], 2u);
+  // tickets are drawn kDraw at a time and one draw ahead: lane 0 keeps the pending result in a register and the warp
+  // only reads it (shuffle) when the current batch is used up, so the atomic's round trip overlaps those items
+  constexpr unsigned kDraw = 4;
+  unsigned pending = 0;
+  if (lane == 0) pending = atomicAdd(&P.ctr[0], kDraw);
+  unsigned cur = __shfl_sync(0xffffffffu, pending, 0);
   for (;;) {
-    const unsigned nxt = atomicAdd(&P.ctr[0], 2u);
-    for (unsigned ticket = cur; ticket < cur + 2u; ++ticket) {
-      while (seg < nseg && ticket >= seg_start + seg_size(seg)) { seg_start += seg_size(seg); ++seg; }
+    if (lane == 0) pending = atomicAdd(&P.ctr[0], kDraw);
+    for (unsigned ticket = cur; ticket < cur + kDraw; ++ticket) {
+      while (ticket >= seg_end) next_segment();
       if (seg >= nseg) {  // queue exhausted: finish the bookkeeping, then tell the workers
         retire(uses);
         flush(true);
-        for (int s_ = 0; s_ < P.slots; ++s_) {  // every slot has its own worker warps
-          metas[s_].kind = kItemStop;
-          u_mbar_arrive(&full[s_]);
+        if (lane == 0) {
+          for (int s_ = 0; s_ < P.slots; ++s_) {  // every slot group waits on its own barrier
+            metas[s_].kind = kItemStop;
+            u_mbar_arrive(&full[s_]);
+          }
+          if (timing) { st_cycles[2] = c_empty; st_cycles[3] = c_dep; st_cycles[1] = uses; }
         }
-        if (st_cycles) { st_cycles[2] = c_empty; st_cycles[3] = c_dep; st_cycles[1] = uses; }
+        __syncwarp();
         return;
       }
-      const long long t0 = st_cycles ? clk() : 0;
+      const long long t0 = timing ? clk() : 0;
       if (uses >= (unsigned)P.slots) retire(uses - (unsigned)P.slots + 1u);  // frees this item's slot
-      retire_ready();
-      if (!(seg & 1) && seg_tile(seg) - flush_tile >= 15) retire(uses);  // keep the & 15 bookkeeping window valid
-      flush(false);
-      const long long t1 = st_cycles ? clk() : 0;
-      SlotMeta m;
-      const int t = seg_tile(seg);
-      const unsigned idx = ticket - seg_start;
-      const unsigned chunks = (unsigned)((size_t)tile_rows(P, t) * P.c / P.p);
-      m.kind = (seg & 1) ? kItemS : kItemR;
-      m.mod = idx >= chunks ? 1 : 0;
-      m.tile = t;
-      m.q0 = (int)((size_t)t * planes_per_tile + (size_t)(idx - (m.mod ? chunks : 0u)) * P.p);
-      {  // first plane of the chunk = sample n, channel c0 (a chunk never straddles samples: P divides C)
-        const int n_ = m.q0 / P.c;
-        m.rofs = n_ * P.rout_ld + (m.q0 - n_ * P.c);
+      if (seg > 2 * flush_tile) {  // a finished R stage is waiting to be published (else nothing to do: skip the polls)
+        retire_ready();
+        flush(false);
       }
-      m.pad0 = m.pad1 = m.pad2 = 0;
-      if (m.kind == kItemS) {
-        if (ld_acquire_u32(tile_ctr(P, t) + 2) < need_f2) {
-          // about to block: everything this CTA still owes the R counters must be published first
-          retire(uses);
-          flush(false);
-          wait_counter(tile_ctr(P, t) + 2, need_f2);
+      if (seg_kind == kItemR && seg_t - flush_tile >= 4) {  // keep the four-tile bookkeeping window valid
+        retire(uses);
+        flush(false);
+      }
+      const long long t1 = timing ? clk() : 0;
+      const unsigned idx = ticket - seg_start;
+      const int mod = idx >= seg_chunks ? 1 : 0;
+      const unsigned ch = idx - (mod ? seg_chunks : 0u);
+      const int q0 = seg_qbase + (int)ch * P.p;
+      if (seg_kind == kItemS && seg_t > ready_tile) {
+        if (!P.nodeps) {
+          bool ok = ld_acquire_u32(tile_ctr(P, seg_t) + 2) >= need_f2;
+          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+          if (!ok) {
+            // about to block: everything this CTA still owes the R counters must be published first
+            retire(uses);
+            flush(false);
+            wait_counter(tile_ctr(P, seg_t) + 2, need_f2);
+          }
         }
+        ready_tile = seg_t;
         asm volatile("fence.proxy.async;" ::: "memory");  // the gates were written through the generic proxy
       }
-      const long long t2 = st_cycles ? clk() : 0;
+      const long long t2 = timing ? clk() : 0;
       c_empty += t1 - t0; c_dep += t2 - t1;
-      metas[slot] = m;
-      rec_tile[slot] = m.kind == kItemR ? t : -1;
-      if (m.kind == kItemR) issued[t & 15]++;
-      const size_t off = (size_t)m.q0 * P.hw;
-      const uint32_t vec_bytes = (uint32_t)P.p * 4u;
-      if (m.kind == kItemR) {
+      if (lane == 0) {
+        // first plane of the chunk = sample n, channel c0 (a chunk never straddles samples: P divides C)
+        const int nl = P.cps == 1 ? (int)ch : (int)__umulhi(ch, P.cps_magic);  // ch / cps
+        SlotMeta m;
+        m.kind = seg_kind; m.mod = mod; m.tile = seg_t; m.q0 = q0;
+        m.rofs = (seg_n0 + nl) * P.rout_ld + ((int)ch - nl * P.cps) * P.p;
+        m.pad0 = m.pad1 = m.pad2 = 0;
+        *reinterpret_cast<int4*>(&metas[slot]) = make_int4(m.kind, m.mod, m.tile, m.q0);
+        metas[slot].rofs = m.rofs;
+      }
+      __syncwarp();
+      rec = (rec & ~(0xffull << (8 * slot))) |
+            ((unsigned long long)(seg_kind == kItemR ? (0x80u | ((unsigned)seg_t & 0x7fu)) : 0u) << (8 * slot));
+      if (seg_kind == kItemR) iss += 1ull << (16 * (seg_t - flush_tile));
+      const size_t off = (size_t)q0 * P.hw;
+      const uint32_t sbase = smem0 + (uint32_t)slot * P.slot_bytes, bar = full0 + (uint32_t)slot * 8u;
+      const uint32_t sgate = sbase + (uint32_t)P.nbuf * P.chunk_bytes;
+      if (seg_kind == kItemR) {
         if (P.bwd) {
-          mbar_expect_tx(&full[slot], 2 * P.chunk_bytes + vec_bytes);
-          bulk_g2s(sm.chunk(slot, 0), P.x[m.mod] + off, P.chunk_bytes, &full[slot], pol_keep);
-          bulk_g2s(sm.chunk(slot, 1), P.y[m.mod] + off, P.chunk_bytes, &full[slot], pol_drop);
-          bulk_g2s(sm.gate(slot, P.nbuf), P.gate[m.mod] + m.q0, vec_bytes, &full[slot], pol_keep);
+          mbar_expect_tx_el(bar, 2 * P.chunk_bytes + vec_bytes);
+          bulk_g2s_elect(sbase, P.x[mod] + off, P.chunk_bytes, bar, pol_keep);
+          bulk_g2s_elect(sbase + P.chunk_bytes, P.y[mod] + off, P.chunk_bytes, bar, pol_drop);
+          bulk_g2s_elect(sgate, P.gate[mod] + q0, vec_bytes, bar, pol_keep);
         } else {
-          mbar_expect_tx(&full[slot], P.chunk_bytes);
-          bulk_g2s(sm.chunk(slot, 0), P.x[m.mod] + off, P.chunk_bytes, &full[slot], pol_keep);
+          mbar_expect_tx_el(bar, P.chunk_bytes);
+          bulk_g2s_elect(sbase, P.x[mod] + off, P.chunk_bytes, bar, pol_keep);
         }
       } else {
-        mbar_expect_tx(&full[slot], P.chunk_bytes + vec_bytes * (P.bwd ? 2u : 1u));
-        bulk_g2s(sm.chunk(slot, 0), P.x[m.mod] + off, P.chunk_bytes, &full[slot], pol_drop);
-        bulk_g2s(sm.gate(slot, P.nbuf), P.gate[m.mod] + m.q0, vec_bytes, &full[slot], pol_drop);
-        if (P.bwd) bulk_g2s(sm.add(slot, P.nbuf), P.add[m.mod] + m.q0, vec_bytes, &full[slot], pol_drop);
+        mbar_expect_tx_el(bar, P.chunk_bytes + vec_bytes * (P.bwd ? 2u : 1u));
+        bulk_g2s_elect(sbase, P.x[mod] + off, P.chunk_bytes, bar, pol_drop);
+        bulk_g2s_elect(sgate, P.gate[mod] + q0, vec_bytes, bar, pol_drop);
+        if (P.bwd) bulk_g2s_elect(sgate + vec_bytes, P.add[mod] + q0, vec_bytes, bar, pol_drop);
       }
       ++uses;
       if (++slot == P.slots) slot = 0;
     }
-    cur = nxt;
+    cur = __shfl_sync(0xffffffffu, pending, 0);
   }
 }
 
-// A slot is served by `wps` worker warps (one warp per slot when the ring has 8 slots): different warps work on
-// different items at the same time, so whatever one warp waits for (its result stores before the releasing arrive,
-// shared-memory latency) is hidden behind the other slots' warps.
+// The eight worker warps form groups of `wps` warps; a group owns TWO slots and works on one of them while the TMA
+// fills the other.  Different groups work on different items at the same time, so whatever one group waits for (its
+// result stores before the releasing arrive, shared-memory latency) is hidden behind the others.  Within a warp the
+// loops are written for instruction-level parallelism -- 8 independent 128-bit shared loads per lane before the first
+// add, two planes' shuffle chains interleaved -- because one SM only has these eight warps to hide latency with.
 //
 // plane sums (forward) or <grad_out, input> dots (backward) of the P planes of a chunk; L lanes per plane
-__device__ __forceinline__ void reduce_chunk(const TileParams& P, const SlotMeta& m, const float* b0, const float* b1,
-                                             const float* sgate, int sw, int lane) {
+template <bool BWD>
+__device__ __forceinline__ float plane_partial_vec(const float4* __restrict__ v, const float4* __restrict__ w, int hw4,
+                                                   int lane_in, int L) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int i0 = lane_in; i0 < hw4; i0 += 8 * L) {
+    float4 x[8], y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * L;
+      const bool ok = i < hw4;
+      x[u] = ok ? v[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (BWD) y[u] = ok ? w[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (BWD) {
+        a0 = fmaf(x[u].x, y[u].x, a0); a1 = fmaf(x[u].y, y[u].y, a1);
+        a2 = fmaf(x[u].z, y[u].z, a2); a3 = fmaf(x[u].w, y[u].w, a3);
+      } else {
+        a0 += x[u].x; a1 += x[u].y; a2 += x[u].z; a3 += x[u].w;
+      }
+    }
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+template <bool BWD>
+__device__ __forceinline__ float plane_partial_scalar(const float* __restrict__ v, const float* __restrict__ w, int hw,
+                                                      int lane_in, int L) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int i = lane_in;
+  for (; i + 7 * L < hw; i += 8 * L) {
+    float x[8], y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { x[u] = v[i + u * L]; if (BWD) y[u] = w[i + u * L]; }
+    if (BWD) {
+      a0 = fmaf(x[0], y[0], a0); a1 = fmaf(x[1], y[1], a1); a2 = fmaf(x[2], y[2], a2); a3 = fmaf(x[3], y[3], a3);
+      a0 = fmaf(x[4], y[4], a0); a1 = fmaf(x[5], y[5], a1); a2 = fmaf(x[6], y[6], a2); a3 = fmaf(x[7], y[7], a3);
+    } else {
+      a0 += x[0]; a1 += x[1]; a2 += x[2]; a3 += x[3]; a0 += x[4]; a1 += x[5]; a2 += x[6]; a3 += x[7];
+    }
+  }
+  for (; i < hw; i += L) a0 = BWD ? fmaf(v[i], w[i], a0) : a0 + v[i];
+  return (a0 + a1) + (a2 + a3);
+}
+
+template <bool BWD>
+__device__ __forceinline__ void reduce_chunk_t(const TileParams& P, const SlotMeta& m, const float* b0, const float* b1,
+                                               const float* sgate, int sw, int lane) {
   const int L = P.lanes, lane_in = lane & (L - 1), gpw = 32 >> P.lanes_log2, grp = lane >> P.lanes_log2;
   const int hw = P.hw;
   float* dst = P.rout[m.mod] + m.rofs;
-  // the trip count is uniform over the warp (shuffles below): inactive groups run with `act == false`
-  for (int base = sw * gpw; base < P.p; base += P.wps * gpw) {
-    const int pl = base + grp;
-    const bool act = pl < P.p;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (act) {
-      if ((hw & 3) == 0) {
-        const int hw4 = hw >> 2;
-        const float4* v = reinterpret_cast<const float4*>(b0) + (size_t)pl * hw4;
-        int i = lane_in;
-        if (P.bwd) {
-          const float4* w = reinterpret_cast<const float4*>(b1) + (size_t)pl * hw4;
-          for (; i + L < hw4; i += 2 * L) {
-            const float4 g0 = v[i], x0 = w[i], g1 = v[i + L], x1 = w[i + L];
-            a0 = fmaf(g0.x, x0.x, a0); a1 = fmaf(g0.y, x0.y, a1); a2 = fmaf(g0.z, x0.z, a2); a3 = fmaf(g0.w, x0.w, a3);
-            a0 = fmaf(g1.x, x1.x, a0); a1 = fmaf(g1.y, x1.y, a1); a2 = fmaf(g1.z, x1.z, a2); a3 = fmaf(g1.w, x1.w, a3);
-          }
-          if (i < hw4) {
-            const float4 g0 = v[i], x0 = w[i];
-            a0 = fmaf(g0.x, x0.x, a0); a1 = fmaf(g0.y, x0.y, a1); a2 = fmaf(g0.z, x0.z, a2); a3 = fmaf(g0.w, x0.w, a3);
-          }
-        } else {
-          for (; i + 3 * L < hw4; i += 4 * L) {
-            const float4 x0 = v[i], x1 = v[i + L], x2 = v[i + 2 * L], x3 = v[i + 3 * L];
-            a0 += x0.x; a1 += x0.y; a2 += x0.z; a3 += x0.w;
-            a0 += x1.x; a1 += x1.y; a2 += x1.z; a3 += x1.w;
-            a0 += x2.x; a1 += x2.y; a2 += x2.z; a3 += x2.w;
-            a0 += x3.x; a1 += x3.y; a2 += x3.z; a3 += x3.w;
-          }
-          for (; i < hw4; i += L) {
-            const float4 x0 = v[i];
-            a0 += x0.x; a1 += x0.y; a2 += x0.z; a3 += x0.w;
-          }
-        }
-      } else {
-        const float* v = b0 + (size_t)pl * hw;
-        const float* w = b1 + (size_t)pl * hw;
-        int i = lane_in;
-        if (P.bwd) {
-          for (; i + 3 * L < hw; i += 4 * L) {
-            a0 = fmaf(v[i], w[i], a0); a1 = fmaf(v[i + L], w[i + L], a1);
-            a2 = fmaf(v[i + 2 * L], w[i + 2 * L], a2); a3 = fmaf(v[i + 3 * L], w[i + 3 * L], a3);
-          }
-          for (; i < hw; i += L) a0 = fmaf(v[i], w[i], a0);
-        } else {
-          for (; i + 3 * L < hw; i += 4 * L) { a0 += v[i]; a1 += v[i + L]; a2 += v[i + 2 * L]; a3 += v[i + 3 * L]; }
-          for (; i < hw; i += L) a0 += v[i];
-        }
-      }
+  const int stride = P.wps * gpw;
+  // two planes per iteration (independent load / shuffle chains); the trip count is uniform over the warp
+  for (int base = sw * gpw; base < P.p; base += 2 * stride) {
+    const int pl0 = base + grp, pl1 = pl0 + stride;
+    const bool act0 = pl0 < P.p, act1 = pl1 < P.p;
+    float t0 = 0.f, t1 = 0.f;
+    if ((hw & 3) == 0) {
+      const int hw4 = hw >> 2;
+      const float4* v = reinterpret_cast<const float4*>(b0);
+      const float4* w = reinterpret_cast<const float4*>(b1);
+      if (act0) t0 = plane_partial_vec<BWD>(v + (size_t)pl0 * hw4, w + (size_t)pl0 * hw4, hw4, lane_in, L);
+      if (act1) t1 = plane_partial_vec<BWD>(v + (size_t)pl1 * hw4, w + (size_t)pl1 * hw4, hw4, lane_in, L);
+    } else {
+      if (act0) t0 = plane_partial_scalar<BWD>(b0 + (size_t)pl0 * hw, b1 + (size_t)pl0 * hw, hw, lane_in, L);
+      if (act1) t1 = plane_partial_scalar<BWD>(b0 + (size_t)pl1 * hw, b1 + (size_t)pl1 * hw, hw, lane_in, L);
     }
-    float t = (a0 + a1) + (a2 + a3);
-    for (int o = L >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (act && lane_in == 0) {
-      if (P.bwd) {
-        const float g = sgate[pl];
-        dst[pl] = t * P.gate_scale * g * (1.f - g);   // dE = dg * g (1 - g)
+    for (int o = L >> 1; o > 0; o >>= 1) {
+      t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+    }
+    if (lane_in == 0) {
+      if (BWD) {
+        if (act0) { const float g = sgate[pl0]; dst[pl0] = t0 * P.gate_scale * g * (1.f - g); }  // dE = dg * g (1 - g)
+        if (act1) { const float g = sgate[pl1]; dst[pl1] = t1 * P.gate_scale * g * (1.f - g); }
       } else {
-        dst[pl] = t / (float)hw;                       // squeeze
+        if (act0) dst[pl0] = t0 / (float)hw;   // squeeze
+        if (act1) dst[pl1] = t1 / (float)hw;
       }
     }
   }
@@ -397,42 +480,40 @@ __device__ __forceinline__ int plane_of(unsigned e, const TileParams& P) {
   return P.hw == 1 ? (int)e : (int)__umulhi(e, P.hw_magic);
 }
 
-// out = x * (gate * gate_scale) [+ add]: flat 128-bit walk over the chunk, the plane of an element from its index
-__device__ __forceinline__ void scale_chunk(const TileParams& P, const SlotMeta& m, const float* b0, const float* sgate,
-                                            const float* sadd, int sw, int lane) {
+// out = x * (gate * gate_scale) [+ add]: flat 128-bit walk over the chunk, the plane of an element from its index;
+// four independent vectors per lane in flight
+template <bool BWD>
+__device__ __forceinline__ void scale_chunk_t(const TileParams& P, const SlotMeta& m, const float* b0, const float* sgate,
+                                              const float* sadd, int sw, int lane) {
   const int hw = P.hw;
   const int nvec = (int)(P.chunk_bytes >> 4);
   const int step = 32 * P.wps;
   const float4* v = reinterpret_cast<const float4*>(b0);
   float4* o = reinterpret_cast<float4*>(P.out[m.mod] + (size_t)m.q0 * hw);
   const float gs = P.gate_scale;
-  if ((hw & 3) == 0) {
-#pragma unroll 4
-    for (int i = sw * 32 + lane; i < nvec; i += step) {
-      const int pl = plane_of((unsigned)(4 * i), P);
-      const float sc = sgate[pl] * gs;
-      float4 x = v[i];
-      if (P.bwd) {
-        const float ad = sadd[pl];
-        x.x = fmaf(x.x, sc, ad); x.y = fmaf(x.y, sc, ad); x.z = fmaf(x.z, sc, ad); x.w = fmaf(x.w, sc, ad);
-      } else {
-        x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
-      }
-      stg_stream(o + i, x);
+  const bool vec_planes = (hw & 3) == 0;
+  for (int i0 = sw * 32 + lane; i0 < nvec; i0 += 4 * step) {
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * step;
+      x[u] = i < nvec ? v[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else {
-#pragma unroll 2
-    for (int i = sw * 32 + lane; i < nvec; i += step) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * step;
+      if (i >= nvec) break;
       const unsigned e = 4u * (unsigned)i;
-      const int p0 = plane_of(e, P), p1 = plane_of(e + 1, P), p2 = plane_of(e + 2, P), p3 = plane_of(e + 3, P);
-      float4 x = v[i];
-      if (P.bwd) {
-        x.x = fmaf(x.x, sgate[p0] * gs, sadd[p0]); x.y = fmaf(x.y, sgate[p1] * gs, sadd[p1]);
-        x.z = fmaf(x.z, sgate[p2] * gs, sadd[p2]); x.w = fmaf(x.w, sgate[p3] * gs, sadd[p3]);
+      const int p0 = plane_of(e, P);
+      int p1 = p0, p2 = p0, p3 = p0;
+      if (!vec_planes) { p1 = plane_of(e + 1, P); p2 = plane_of(e + 2, P); p3 = plane_of(e + 3, P); }
+      if (BWD) {
+        x[u].x = fmaf(x[u].x, sgate[p0] * gs, sadd[p0]); x[u].y = fmaf(x[u].y, sgate[p1] * gs, sadd[p1]);
+        x[u].z = fmaf(x[u].z, sgate[p2] * gs, sadd[p2]); x[u].w = fmaf(x[u].w, sgate[p3] * gs, sadd[p3]);
       } else {
-        x.x *= sgate[p0] * gs; x.y *= sgate[p1] * gs; x.z *= sgate[p2] * gs; x.w *= sgate[p3] * gs;
+        x[u].x *= sgate[p0] * gs; x[u].y *= sgate[p1] * gs; x[u].z *= sgate[p2] * gs; x[u].w *= sgate[p3] * gs;
       }
-      stg_stream(o + i, x);
+      stg_stream(o + i, x[u]);
     }
   }
 }
@@ -444,8 +525,10 @@ __device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
 __device__ void stream_workers(const TileParams& P, const StreamSmem& sm, const SlotMeta* metas, uint64_t* full,
                                uint64_t* empty, int tid, long long* st_cycles) {
   const int lane = tid & 31, warp = tid >> 5;
-  const int slot = warp / P.wps, sw = warp - slot * P.wps;
-  uint32_t phase = 0;
+  const int groups = P.slots >> 1;
+  const int grp = warp / P.wps, sw = warp - grp * P.wps;
+  int slot = grp;            // this group's slots: grp and grp + groups, used alternately
+  uint32_t phase = 0;        // both slots are on the same use number until the second one has been consumed
   long long c_wait = 0, c_red = 0, c_scale = 0;
   const bool timing = st_cycles != nullptr && tid == 0;
   for (;;) {
@@ -454,12 +537,18 @@ __device__ void stream_workers(const TileParams& P, const StreamSmem& sm, const 
     const long long t1 = timing ? clk() : 0;
     const SlotMeta m = metas[slot];
     if (m.kind == kItemStop) break;
-    if (m.kind == kItemR) {
-      reduce_chunk(P, m, sm.chunk(slot, 0), sm.chunk(slot, 1), sm.gate(slot, P.nbuf), sw, lane);
+    if (P.nodeps >= 2) {  // measurement only: no compute, just recycle the slot
+      if (P.nodeps == 3 && lane == 0) { volatile float sink = sm.chunk(slot, 0)[tid]; (void)sink; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(&empty[slot]);
+    } else if (m.kind == kItemR) {
+      if (P.bwd) reduce_chunk_t<true>(P, m, sm.chunk(slot, 0), sm.chunk(slot, 1), sm.gate(slot, P.nbuf), sw, lane);
+      else reduce_chunk_t<false>(P, m, sm.chunk(slot, 0), sm.chunk(slot, 1), sm.gate(slot, P.nbuf), sw, lane);
       __syncwarp();
       if (lane == 0) u_mbar_arrive(&empty[slot]);  // release.cta: the loader publishes the R results after its wait
     } else {
-      scale_chunk(P, m, sm.chunk(slot, 0), sm.gate(slot, P.nbuf), sm.add(slot, P.nbuf), sw, lane);
+      if (P.bwd) scale_chunk_t<true>(P, m, sm.chunk(slot, 0), sm.gate(slot, P.nbuf), sm.add(slot, P.nbuf), sw, lane);
+      else scale_chunk_t<false>(P, m, sm.chunk(slot, 0), sm.gate(slot, P.nbuf), sm.add(slot, P.nbuf), sw, lane);
       __syncwarp();
       // nothing to publish: the arrival only says that this warp's shared-memory reads are done (their values
       // have been consumed by the stores issued above)
@@ -470,7 +559,8 @@ __device__ void stream_workers(const TileParams& P, const StreamSmem& sm, const 
       c_wait += t1 - t0;
       if (m.kind == kItemR) c_red += t2 - t1; else c_scale += t2 - t1;
     }
-    phase ^= 1u;
+    if (slot == grp) slot = grp + groups;
+    else { slot = grp; phase ^= 1u; }
   }
   if (timing) { st_cycles[4] = c_wait; st_cycles[5] = c_red; st_cycles[6] = c_scale; }
 }
@@ -483,11 +573,21 @@ struct GemmBars { uint64_t* raw; uint64_t* full; uint64_t* empty; uint64_t* acc_
 struct GemmItem { int stage, tile, ntile, split; };
 
 // 2-D TMA tile load: box (32 k x 32 rows) of an fp32 [rows, K] tensor -> shared memory, SWIZZLE_128B
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int k, int row, uint64_t* bar) {
+// (called by all 32 lanes of a converged warp; one elected lane issues)
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map, int k, int row, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          u_smem_addr(dst)),
-      "l"(map), "r"(k), "r"(row), "r"(u_smem_addr(bar))
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+      ::"r"(dst), "l"(map), "r"(k), "r"(row), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(bar), "r"(bytes)
       : "memory");
 }
 
@@ -502,59 +602,58 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const GemmStage& g, const GemmItem& it,
                                                    unsigned char* u_smem, const GemmBars& bars, uint32_t tmem,
                                                    uint32_t kbase, uint32_t gbase, int nk, float (&sum)[64], int warp,
-                                                   int lane, int tid) {
+                                                   int lane, int tid, long long* dbg) {  // (kbase, gbase, nk by value)
   const int m0 = it.tile * P.m_tile;
   const int n0 = it.ntile * UN;
   const int k_begin = it.split * g.k_per_split;
   if (warp == U_PRODUCERS / 32) {
-    // ===== control thread: TMA producer + MMA issuer ============================================================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-      auto issue_tma = [&](int kt) {
-        const uint32_t KT = kbase + (uint32_t)kt, stage = KT % USTAGES;
-        // the stage was last read by the MMAs of k-tile KT - USTAGES
-        if (KT >= (uint32_t)USTAGES) u_mbar_wait(&bars.empty[stage], ((KT / USTAGES) - 1u) & 1u);
-        unsigned char* st = u_smem + stage * U_STAGE_BYTES;
-        mbar_expect_tx(&bars.raw[stage], 2u * U_TILE_BYTES);
-        const int k0 = k_begin + kt * UK;
-        const bool second = g.k_split && k0 >= g.k_split;
-        const CUtensorMap* ma = second ? &g.tm_a2 : &g.tm_a;
-        const int ka = second ? k0 - g.k_split : k0;
+    // ===== control warp: TMA producer + MMA issuer (all 32 lanes converged, see umma.cuh) =========================
+    const uint32_t ub = 0xffffffffu;
+    kbase = __shfl_sync(ub, kbase, 0); gbase = __shfl_sync(ub, gbase, 0); nk = __shfl_sync(ub, nk, 0);
+    const int um0 = __shfl_sync(ub, m0, 0), un0 = __shfl_sync(ub, n0, 0), uk0 = __shfl_sync(ub, k_begin, 0);
+    const uint32_t utmem = __shfl_sync(ub, tmem, 0);
+    const uint32_t smem_base = __shfl_sync(ub, u_smem_addr(u_smem), 0);
+    const uint32_t bar_raw = __shfl_sync(ub, u_smem_addr(bars.raw), 0);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+    const int k_split = g.k_split, n_split = g.n_split;
+    auto issue_tma = [&](int kt) {
+      const uint32_t KT = kbase + (uint32_t)kt, stage = KT % USTAGES;
+      // the stage was last read by the MMAs of k-tile KT - USTAGES
+      if (KT >= (uint32_t)USTAGES) u_mbar_wait(&bars.empty[stage], ((KT / USTAGES) - 1u) & 1u);
+      const uint32_t st = smem_base + stage * U_STAGE_BYTES, bar = bar_raw + stage * 8u;
+      mbar_expect_tx_elect(bar, 2u * U_TILE_BYTES);
+      const int k0 = uk0 + kt * UK;
+      const bool second = k_split && k0 >= k_split;
+      const CUtensorMap* ma = second ? &g.tm_a2 : &g.tm_a;
+      const int ka = second ? k0 - k_split : k0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_2d(st + j * 4096, ma, ka, m0 + 32 * j, &bars.raw[stage]);
+      for (int j = 0; j < 4; ++j) tma_load_2d_elect(st + j * 4096, ma, ka, um0 + 32 * j, bar);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = n0 + 32 * j;
-          const bool hi = r >= g.n_split;
-          tma_load_2d(st + 2 * U_TILE_BYTES + j * 4096, hi ? &g.tm_b2 : &g.tm_b, k0, hi ? r - g.n_split : r,
-                      &bars.raw[stage]);
-        }
-      };
-      const int npre = nk < USTAGES ? nk : USTAGES;
-      for (int s = 0; s < npre; ++s) issue_tma(s);
-      for (int kt = 0; kt < nk; ++kt) {
-        const uint32_t KT = kbase + (uint32_t)kt, GI = gbase + (uint32_t)(kt / UGROUP);
-        const uint32_t stage = KT % USTAGES, b = GI & 1u;
-        if (kt % UGROUP == 0 && GI >= 2) u_mbar_wait(&bars.acc_empty[b], ((GI >> 1) - 1u) & 1u);
-        u_mbar_wait(&bars.full[stage], (KT / USTAGES) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_big = u_smem_addr(u_smem + stage * U_STAGE_BYTES), a_small = a_big + U_TILE_BYTES;
-        const uint32_t b_big = a_big + 2 * U_TILE_BYTES, b_small = a_big + 3 * U_TILE_BYTES;
-        const uint32_t acc = tmem + b * (uint32_t)UN;
-#pragma unroll
-        for (int j = 0; j < UK / 8; ++j) {
-          const uint32_t o = (uint32_t)j * 32u;
-          const uint64_t da_b = u_desc(a_big + o), da_s = u_desc(a_small + o);
-          const uint64_t db_b = u_desc(b_big + o), db_s = u_desc(b_small + o);
-          u_mma_tf32(acc, da_s, db_b, idesc, (kt % UGROUP != 0 || j != 0) ? 1u : 0u);
-          u_mma_tf32(acc, da_b, db_s, idesc, 1u);
-          u_mma_tf32(acc, da_b, db_b, idesc, 1u);
-        }
-        u_commit(&bars.empty[stage]);
-        if (kt % UGROUP == UGROUP - 1 || kt == nk - 1) u_commit(&bars.acc_full[b]);
-        // refill the stage of the PREVIOUS k-tile (its MMAs finish while the ones just queued run)
-        if (kt >= 1 && kt - 1 + USTAGES < nk) issue_tma(kt - 1 + USTAGES);
+      for (int j = 0; j < 4; ++j) {
+        const int r = un0 + 32 * j;
+        const bool hi = r >= n_split;
+        tma_load_2d_elect(st + 2 * U_TILE_BYTES + j * 4096, hi ? &g.tm_b2 : &g.tm_b, k0, hi ? r - n_split : r, bar);
       }
+    };
+    const int npre = nk < USTAGES ? nk : USTAGES;
+    long long c0 = dbg ? clk() : 0;
+    for (int s = 0; s < npre; ++s) issue_tma(s);
+    if (dbg && lane == 0) { const long long c1 = clk(); dbg[2] += c1 - c0; }
+    for (int kt = 0; kt < nk; ++kt) {
+      const uint32_t KT = kbase + (uint32_t)kt, GI = gbase + (uint32_t)(kt / UGROUP);
+      const uint32_t stage = KT % USTAGES, b = GI & 1u;
+      c0 = dbg ? clk() : 0;
+      if (kt % UGROUP == 0 && GI >= 2) u_mbar_wait(&bars.acc_empty[b], ((GI >> 1) - 1u) & 1u);
+      u_mbar_wait(&bars.full[stage], (KT / USTAGES) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const long long c1 = dbg ? clk() : 0;
+      u_mma_stage_elect(smem_base, stage * U_STAGE_BYTES, utmem + b * (uint32_t)UN, kt % UGROUP == 0, idesc);
+      u_commit_elect(&bars.empty[stage]);
+      if (kt % UGROUP == UGROUP - 1 || kt == nk - 1) u_commit_elect(&bars.acc_full[b]);
+      const long long c2 = dbg ? clk() : 0;
+      // refill the stage of the PREVIOUS k-tile (its MMAs finish while the ones just queued run)
+      if (kt >= 1 && kt - 1 + USTAGES < nk) issue_tma(kt - 1 + USTAGES);
+      if (dbg && lane == 0) { const long long c3 = clk(); dbg[0] += c1 - c0; dbg[1] += c2 - c1; dbg[2] += c3 - c2; }
     }
     __syncwarp();
     return;
@@ -579,9 +678,12 @@ __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const Ge
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     u_mbar_arrive(&bars.acc_empty[b]);
   };
+  const bool wdbg = dbg != nullptr && tid == 0;
   for (int kt = 0; kt < nk; ++kt) {
     const uint32_t KT = kbase + (uint32_t)kt, stage = KT % USTAGES;
+    const long long w0 = wdbg ? clk() : 0;
     u_mbar_wait(&bars.raw[stage], (KT / USTAGES) & 1u);
+    const long long w1 = wdbg ? clk() : 0;
     unsigned char* st = u_smem + stage * U_STAGE_BYTES;
     // small = x - (x with the low 13 mantissa bits cleared), same layout as the raw tile: a linear pass
 #pragma unroll
@@ -603,9 +705,13 @@ __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const Ge
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA unit
     u_mbar_arrive(&bars.full[stage]);
+    const long long w2 = wdbg ? clk() : 0;
     if (kt % UGROUP >= 1 && drained < kt / UGROUP) { drain(drained); ++drained; }
+    if (wdbg) { const long long w3 = clk(); dbg[4] += w1 - w0; dbg[5] += w2 - w1; dbg[6] += w3 - w2; }
   }
+  const long long w4 = wdbg ? clk() : 0;
   while (drained < ngroups) { drain(drained); ++drained; }
+  if (wdbg) dbg[6] += clk() - w4;
 }
 
 // Epilogue.  The accumulators first go through shared memory (the operand stages are idle by then) so that
@@ -802,7 +908,8 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     const int k_end = min(g.k_total, k_begin + g.k_per_split);
     const int nk = k_end > k_begin ? (k_end - k_begin + UK - 1) / UK : 0;
     const long long tg1 = timing ? clk() : 0;
-    gemm_item_mainloop(P, g, it, u_smem, bars, tmem, kbase, gbase, nk, sum, warp, lane, tid);
+    gemm_item_mainloop(P, g, it, u_smem, bars, tmem, kbase, gbase, nk, sum, warp, lane, tid,
+                       st_cycles ? P.stats + (size_t)(gridDim.x + blockIdx.x) * 16 : nullptr);
     const long long tg2 = timing ? clk() : 0;
     kbase += (uint32_t)nk;
     gbase += (uint32_t)((nk + UGROUP - 1) / UGROUP);
@@ -902,8 +1009,7 @@ __global__ void __launch_bounds__(kThreads, 1) tile_pipeline_kernel(const __grid
   __syncthreads();
   StreamSmem sm{smem, P.slot_bytes, P.chunk_bytes, P.p};
   if (tid >= U_PRODUCERS) {
-    if (tid == U_PRODUCERS) stream_loader(P, sm, s_meta, s_full, s_empty, st_cycles);
-    __syncwarp();
+    stream_loader(P, sm, s_meta, s_full, s_empty, st_cycles, tid & 31);
   } else {
     stream_workers(P, sm, s_meta, s_full, s_empty, tid, st_cycles);
     if (st_cycles && tid == 0) { st_cycles[0] = 0; st_cycles[7] = clk() - t_begin; }
@@ -950,7 +1056,7 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   int lanes = 1, lg = 0;
   if (hw % 4 == 0) {
     const int hw4 = hw / 4;
-    while (lanes < 32 && lanes * 6 <= hw4) { lanes *= 2; ++lg; }
+    while (lanes < 32 && lanes * 8 < hw4) { lanes *= 2; ++lg; }   // <= 8 vectors per lane: one batch of loads
     if (lanes < 8 && hw4 >= 8) { lanes = 8; lg = 3; }
   } else {
     while (lanes < 32 && lanes * 64 < hw) { lanes *= 2; ++lg; }
@@ -963,9 +1069,9 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   const size_t budget = 224 * 1024 - 1024;
   int slots = (int)(budget / f.slot_bytes);
   if (slots < 2) return false;
-  slots = slots >= 8 ? 8 : (slots >= 4 ? 4 : 2);  // a power of two: 8 / slots worker warps serve one slot
+  slots = slots >= 8 ? 8 : (slots >= 4 ? 4 : 2);  // a power of two; a group of warps owns two slots
   f.slots = slots;
-  f.wps = (U_PRODUCERS / 32) / slots;
+  f.wps = (U_PRODUCERS / 32) / (slots / 2);
   size_t sm = (size_t)slots * f.slot_bytes;
   if (sm < gemm_smem) sm = gemm_smem;
   f.smem_bytes = sm + 1024;
@@ -1000,10 +1106,10 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   if (g <= 0) {
     const double step_us = (double)f.m_tile * per_sample * (bwd ? 3.0 : 2.0) / 6.5e6;
     g = (int)(units * 0.6 / (step_us > 0.1 ? step_us : 0.1)) + 2;
-    if (g > 40) g = 40;
+    if (g > 56) g = 56;
   }
   const int sms = sm_count();
-  if (g > sms / 3) g = sms / 3;
+  if (g > sms / 2) g = sms / 2;
   if (g < 1) g = 1;
   f.n_gemm = g;
   *o = f;
@@ -1046,6 +1152,9 @@ void fill_common(TileParams& P, const TileCfg& f, int n, int c, int hw, int d, b
   P.m_tile = f.m_tile; P.n_tiles = f.n_tiles; P.p = f.p; P.lanes = f.lanes; P.lanes_log2 = f.lanes_log2; P.lag = f.lag;
   P.n_gemm = f.n_gemm; P.slots = f.slots; P.wps = f.wps; P.nbuf = f.nbuf; P.chunk_bytes = f.chunk_bytes; P.slot_bytes = f.slot_bytes;
   P.hw_magic = (uint32_t)(((1ull << 32) + (unsigned)hw - 1) / (unsigned)hw);
+  P.cps = c / f.p;
+  P.cps_magic = P.cps == 1 ? 0u : (uint32_t)(((1ull << 32) + (unsigned)P.cps - 1) / (unsigned)P.cps);
+  P.slots_log2 = f.slots == 8 ? 3 : (f.slots == 4 ? 2 : 1);
   P.ctr = reinterpret_cast<unsigned*>(ws);
   P.part = reinterpret_cast<float*>(static_cast<char*>(ws) + f.ctr_bytes);
   P.part_tile_floats = f.part_tile_floats;
@@ -1057,6 +1166,7 @@ void fill_common(TileParams& P, const TileCfg& f, int n, int c, int hw, int d, b
   }
   P.n_cs = 0;
   P.stats = g_tile_stats;
+  P.nodeps = g_tile_nodeps;
   P.w_cat_t = nullptr; P.w_sq_t = nullptr; P.w_v = P.w_s = P.w_sq = nullptr;
 }
 

@@ -61,6 +61,44 @@ __device__ __forceinline__ void u_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- warp-converged issue ------------------------------------------------------------------------------------------
+// tcgen05.mma / commit / TMA take their operands from UNIFORM registers.  Measured on B200 (scripts/micro/umma_rate.cu):
+// when the issuing code sits in a divergent region (`if (lane == 0) { ... }`) the compiler wraps every MMA in an
+// ELECT / R2UR.BROADCAST / branch loop and one MMA issues per ~170 cycles whatever its shape; when the WHOLE warp
+// runs the issue sequence converged and one lane is elected INSIDE the instruction's own asm block, the operand moves
+// are software-pipelined and a 128x128x8 TF32 MMA issues every 64 cycles -- the tensor pipe's rate.
+// All functions below must be called by all 32 lanes of a converged warp.
+__device__ __forceinline__ void u_mma_tf32_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void u_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(u_smem_addr(bar))
+      : "memory");
+}
+// the 12 MMAs (4 k-steps x {small*big, big*small, big*big}) of one 32-k operand stage at byte offset `stage_off`
+__device__ __forceinline__ void u_mma_stage_elect(uint32_t smem_base, uint32_t stage_off, uint32_t acc, bool first,
+                                                  uint32_t idesc) {
+  const uint32_t a_big = smem_base + stage_off, a_small = a_big + U_TILE_BYTES;
+  const uint32_t b_big = a_big + 2 * U_TILE_BYTES, b_small = a_big + 3 * U_TILE_BYTES;
+#pragma unroll
+  for (int j = 0; j < UK / 8; ++j) {
+    const uint32_t o = (uint32_t)j * 32u;  // 8 k further inside the 128-byte rows
+    u_mma_tf32_elect(acc, u_desc(a_small + o), u_desc(b_big + o), idesc, (j != 0 || !first) ? 1u : 0u);
+    u_mma_tf32_elect(acc, u_desc(a_big + o), u_desc(b_small + o), idesc, 1u);
+    u_mma_tf32_elect(acc, u_desc(a_big + o), u_desc(b_big + o), idesc, 1u);
+  }
+}
+
 __device__ __forceinline__ void u_tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(

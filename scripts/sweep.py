@@ -38,6 +38,21 @@ VARIANTS = {
     "tile_g32": (L.F_FORCE_TILE, {"tile_gemm_ctas": 32}),
     "tile_g40": (L.F_FORCE_TILE, {"tile_gemm_ctas": 40}),
     "tile_c14": (L.F_FORCE_TILE, {"tile_chunk_kb": 14}),
+    "tile_nodeps": (L.F_FORCE_TILE, {"tile_nodeps": 1, "tile_gemm_ctas": 8}),
+    "tile_noop": (L.F_FORCE_TILE, {"tile_nodeps": 2, "tile_gemm_ctas": 8}),
+    "tile_noop_c14": (L.F_FORCE_TILE, {"tile_nodeps": 2, "tile_gemm_ctas": 8, "tile_chunk_kb": 14}),
+    "tile_noop_c50": (L.F_FORCE_TILE, {"tile_nodeps": 2, "tile_gemm_ctas": 8, "tile_chunk_kb": 50}),
+    "tile_nodeps_g1": (L.F_FORCE_TILE, {"tile_nodeps": 1, "tile_gemm_ctas": 1}),
+    "t_m16_l4_g8": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 4, "tile_gemm_ctas": 8}),
+    "t_m16_l6_g8": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 6, "tile_gemm_ctas": 8}),
+    "t_m8_l8_g8": (L.F_FORCE_TILE, {"tile_m": 8, "tile_lag": 8, "tile_gemm_ctas": 8}),
+    "t_m32_l3_g8": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 3, "tile_gemm_ctas": 8}),
+    "t_m32_l4_g12": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 4, "tile_gemm_ctas": 12}),
+    "t_m64_l3_g12": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 3, "tile_gemm_ctas": 12}),
+    "t_m64_l4_g16": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 4, "tile_gemm_ctas": 16}),
+    "t_m128_l3_g40": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 3, "tile_gemm_ctas": 40}),
+    "t_m128_l4_g48": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 4, "tile_gemm_ctas": 48}),
+    "t_m128_l2_g48": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 2, "tile_gemm_ctas": 48}),
     "tile_c50": (L.F_FORCE_TILE, {"tile_chunk_kb": 50}),
     "auto_biggemm": (0, {"gemm_big_tiles": 1}),
     "auto_ffma": (0, {"gemm_tf32x3": 0, "gemm_umma": 0}),
@@ -108,8 +123,13 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 2, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 2, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
+                # workspace sizes depend on the tile tunables: re-query for this variant
+                b.ws_bytes = lib.gml_mmtm_bwd_workspace_bytes(b.dims)
+                b.ws = torch.empty(b.ws_bytes, dtype=torch.uint8, device=dev)
+                b.fws_bytes = lib.gml_mmtm_fwd_workspace_bytes(b.dims)
+                b.fws = torch.empty(b.fws_bytes, dtype=torch.uint8, device=dev)
                 rc = fwd(flags)
                 if rc == -5:
                     continue  # unsupported shape for this variant

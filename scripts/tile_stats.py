@@ -24,7 +24,7 @@ def main():
     for kv in filter(None, args.tunables.split(",")):
         k, v = kv.split("=")
         L.check(lib.gml_set_tunable(k.encode(), int(v)))
-    stats = torch.zeros(512 * 16, dtype=torch.int64, device=dev)
+    stats = torch.zeros(1024 * 16, dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     for c, h in SHAPES:
         b = BlockBuffers(torch, L, args.n, c, h, dev, seed=c)
@@ -51,7 +51,10 @@ def main():
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()
             L.check(lib.gml_set_tunable(b"tile_stats_ptr", 0))
-            s = stats.view(-1, 16).cpu().double()
+            s_all = stats.view(-1, 16).cpu().double()
+            nsm = torch.cuda.get_device_properties(0).multi_processor_count
+            s, dbg = s_all[:nsm], s_all[nsm:2 * nsm]
+            dbg = dbg[(s[:, 7] > 0) & (s[:, 0] == 1)]
             s = s[s[:, 7] > 0]
             g, r = s[s[:, 0] == 1], s[s[:, 0] == 0]
             ms = e0.elapsed_time(e1)
@@ -70,6 +73,9 @@ def main():
                           g[:, 4].sum() / max(g[:, 1].sum(), 1) / 1e3))
                 print("        epilogue split: partial+fold %6.0f store %6.0f fence %6.0f sync+signal %6.0f kcyc" % tuple(
                     (g[:, 8 + i].mean() / 1e3) for i in range(4)))
+                if len(dbg):
+                    print("        main loop, control thread: wait-full %6.0f mma-issue %6.0f tma-issue(+empty wait) %6.0f | "
+                          "worker0: wait-raw %6.0f split %6.0f drain %6.0f kcyc" % tuple(dbg[:, i].mean() / 1e3 for i in (0, 1, 2, 4, 5, 6)))
                 print("        warp4 store %6.0f fence %6.0f | warp8 fence %6.0f sync %6.0f kcyc" % tuple(
                     (g[:, 12 + i].mean() / 1e3) for i in range(4)))
         del b
