@@ -252,7 +252,7 @@ extern int g_fused_group_kb;
 extern int g_fused_stash_kb;
 extern int g_tile_kind, g_tile_lag, g_tile_gemm_ctas, g_tile_m, g_tile_chunk_kb, g_tile_min_mb;
 extern long long* g_tile_stats;
-extern int g_tile_nodeps;
+extern int g_tile_nodeps, g_tile_ksplit_tiles;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -283,10 +283,11 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
     if (value < 0 || value > 2) return GML_E_BADARG;
     g_tile_kind = (int)value; return GML_OK;
   }
-  if (!strcmp(name, "tile_lag")) { g_tile_lag = value < 1 ? 1 : (value > 8 ? 8 : (int)value); return GML_OK; }
+  if (!strcmp(name, "tile_lag")) { g_tile_lag = value < 0 ? 0 : (value > 16 ? 16 : (int)value); return GML_OK; }
   if (!strcmp(name, "tile_gemm_ctas")) { g_tile_gemm_ctas = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "tile_m")) { g_tile_m = value < 0 ? 0 : (value > 128 ? 128 : (int)value); return GML_OK; }
   if (!strcmp(name, "tile_chunk_kb")) { g_tile_chunk_kb = value < 1 ? 1 : (value > 100 ? 100 : (int)value); return GML_OK; }
+  if (!strcmp(name, "tile_ksplit_tiles")) { g_tile_ksplit_tiles = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "tile_nodeps")) { g_tile_nodeps = (int)value; return GML_OK; }
   if (!strcmp(name, "tile_stats_ptr")) { g_tile_stats = reinterpret_cast<long long*>(value); return GML_OK; }
   if (!strcmp(name, "tile_min_mb")) { g_tile_min_mb = value < 0 ? 0 : (int)value; return GML_OK; }

@@ -110,6 +110,13 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                : "memory");
 }
 
+// streaming store that also tells L2 to drop the line first (keeps evict_last lines of other streams resident)
+__device__ __forceinline__ void stg_hint(float4* p, const float4& v, uint64_t policy) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "l"(policy)
+               : "memory");
+}
+
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace gml

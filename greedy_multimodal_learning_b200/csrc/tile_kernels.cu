@@ -40,17 +40,19 @@
 namespace gml {
 
 int g_tile_kind = 0;        // tunable "tile_kind": 0 automatic, 1 whenever the shape is supported, 2 never
-int g_tile_lag = 2;         // tunable "tile_lag": tiles between a tile's R and S stage in the stream queue
+int g_tile_lag = 0;         // tunable "tile_lag": tiles between a tile's R and S stage in the stream queue (0 = automatic)
 int g_tile_gemm_ctas = 0;   // tunable "tile_gemm_ctas": 0 = from the FLOP/byte estimate
 int g_tile_m = 0;           // tunable "tile_m": samples per tile, 0 = automatic (~25 MB of feature map per tile)
 int g_tile_chunk_kb = 28;   // tunable "tile_chunk_kb": upper bound of a chunk (one work item) in KB
-int g_tile_min_mb = 8;      // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality
+int g_tile_min_mb = 96;     // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality
+int g_tile_ksplit_tiles = 0;  // tunable "tile_ksplit_tiles": k-tiles per split-K item (0 = no split-K: the deep pipeline hides the
+                            // chain latency, and partial planes + folds cost more GEMM-CTA time than they save)
 int g_tile_nodeps = 0;      // debug/measurement ONLY (wrong results): S items do not wait for the gates
 long long* g_tile_stats = nullptr;  // debug: per-CTA cycle breakdown (device buffer, 16 slots per CTA)
 
 namespace {
 
-constexpr int kThreads = UTHREADS;  // 288: warps 0-7 workers, warp 8 control (loader / MMA issuer)
+constexpr int kThreads = U_PRODUCERS + 64;  // 320: warps 0-7 workers, warp 8 loader / MMA issuer, warp 9 TMA producer (GEMM role)
 constexpr int kMaxSlots = 8;
 constexpr int kMaxNT = 16;          // 128-wide column tiles of a GEMM stage (N <= 2048)
 constexpr int kMaxSplits = 8;
@@ -69,6 +71,7 @@ struct GemmStage {
   alignas(64) CUtensorMap tm_b;    // B rows = output columns
   alignas(64) CUtensorMap tm_b2;   // rows >= n_split come from here (n - n_split)
   int k_split, n_split;
+  int b_box_rows;                  // 128 when a 128-row B tile never straddles n_split (one TMA per tile), else 32
   int n_total, k_total;
   int n_tiles, splits, k_per_split;  // k_per_split is a multiple of UK
   float* out; float* out2;           // column < n_split -> out[row * ldo + col], else out2[row * ldo + col - n_split]
@@ -463,7 +466,7 @@ __device__ __forceinline__ void reduce_chunk_t(const TileParams& P, const SlotMe
       t0 += __shfl_xor_sync(0xffffffffu, t0, o);
       t1 += __shfl_xor_sync(0xffffffffu, t1, o);
     }
-    if (lane_in == 0) {
+    if (lane_in == 0 && (P.nodeps != 4 || t0 == 123.456f)) {
       if (BWD) {
         if (act0) { const float g = sgate[pl0]; dst[pl0] = t0 * P.gate_scale * g * (1.f - g); }  // dE = dg * g (1 - g)
         if (act1) { const float g = sgate[pl1]; dst[pl1] = t1 * P.gate_scale * g * (1.f - g); }
@@ -491,6 +494,7 @@ __device__ __forceinline__ void scale_chunk_t(const TileParams& P, const SlotMet
   const float4* v = reinterpret_cast<const float4*>(b0);
   float4* o = reinterpret_cast<float4*>(P.out[m.mod] + (size_t)m.q0 * hw);
   const float gs = P.gate_scale;
+  const uint64_t pol_out = policy_evict_first();
   const bool vec_planes = (hw & 3) == 0;
   for (int i0 = sw * 32 + lane; i0 < nvec; i0 += 4 * step) {
     float4 x[4];
@@ -513,7 +517,8 @@ __device__ __forceinline__ void scale_chunk_t(const TileParams& P, const SlotMet
       } else {
         x[u].x *= sgate[p0] * gs; x[u].y *= sgate[p1] * gs; x[u].z *= sgate[p2] * gs; x[u].w *= sgate[p3] * gs;
       }
-      stg_stream(o + i, x[u]);
+      if (P.nodeps != 4) stg_hint(o + i, x[u], pol_out);
+      else if (x[u].x == 123.456f) stg_stream(o + i, x[u]);
     }
   }
 }
@@ -537,7 +542,7 @@ __device__ void stream_workers(const TileParams& P, const StreamSmem& sm, const 
     const long long t1 = timing ? clk() : 0;
     const SlotMeta m = metas[slot];
     if (m.kind == kItemStop) break;
-    if (P.nodeps >= 2) {  // measurement only: no compute, just recycle the slot
+    if (P.nodeps == 2 || P.nodeps == 3) {  // measurement only: no compute, just recycle the slot
       if (P.nodeps == 3 && lane == 0) { volatile float sink = sm.chunk(slot, 0)[tid]; (void)sink; }
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(&empty[slot]);
@@ -606,43 +611,49 @@ __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const Ge
   const int m0 = it.tile * P.m_tile;
   const int n0 = it.ntile * UN;
   const int k_begin = it.split * g.k_per_split;
-  if (warp == U_PRODUCERS / 32) {
-    // ===== control warp: TMA producer + MMA issuer (all 32 lanes converged, see umma.cuh) =========================
+  if (warp >= U_PRODUCERS / 32) {
+    // ===== control warps (all 32 lanes converged, see umma.cuh): warp 9 produces (TMA), warp 8 issues the MMAs =======
     const uint32_t ub = 0xffffffffu;
     kbase = __shfl_sync(ub, kbase, 0); gbase = __shfl_sync(ub, gbase, 0); nk = __shfl_sync(ub, nk, 0);
-    const int um0 = __shfl_sync(ub, m0, 0), un0 = __shfl_sync(ub, n0, 0), uk0 = __shfl_sync(ub, k_begin, 0);
-    const uint32_t utmem = __shfl_sync(ub, tmem, 0);
     const uint32_t smem_base = __shfl_sync(ub, u_smem_addr(u_smem), 0);
-    const uint32_t bar_raw = __shfl_sync(ub, u_smem_addr(bars.raw), 0);
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-    const int k_split = g.k_split, n_split = g.n_split;
-    auto issue_tma = [&](int kt) {
-      const uint32_t KT = kbase + (uint32_t)kt, stage = KT % USTAGES;
-      // the stage was last read by the MMAs of k-tile KT - USTAGES
-      if (KT >= (uint32_t)USTAGES) u_mbar_wait(&bars.empty[stage], ((KT / USTAGES) - 1u) & 1u);
-      const uint32_t st = smem_base + stage * U_STAGE_BYTES, bar = bar_raw + stage * 8u;
-      mbar_expect_tx_elect(bar, 2u * U_TILE_BYTES);
-      const int k0 = uk0 + kt * UK;
-      const bool second = k_split && k0 >= k_split;
-      const CUtensorMap* ma = second ? &g.tm_a2 : &g.tm_a;
-      const int ka = second ? k0 - k_split : k0;
+    if (warp == U_PRODUCERS / 32 + 1) {
+      const int um0 = __shfl_sync(ub, m0, 0), un0 = __shfl_sync(ub, n0, 0), uk0 = __shfl_sync(ub, k_begin, 0);
+      const uint32_t bar_raw = __shfl_sync(ub, u_smem_addr(bars.raw), 0);
+      const int k_split = g.k_split, n_split = g.n_split;
+      const bool b_one = g.b_box_rows == 128;
+      long long c0 = dbg ? clk() : 0;
+      for (int kt = 0; kt < nk; ++kt) {
+        const uint32_t KT = kbase + (uint32_t)kt, stage = KT % USTAGES;
+        // the stage was last read by the MMAs of k-tile KT - USTAGES
+        if (KT >= (uint32_t)USTAGES) u_mbar_wait(&bars.empty[stage], ((KT / USTAGES) - 1u) & 1u);
+        const uint32_t st = smem_base + stage * U_STAGE_BYTES, bar = bar_raw + stage * 8u;
+        mbar_expect_tx_elect(bar, 2u * U_TILE_BYTES);
+        const int k0 = uk0 + kt * UK;
+        const bool second = k_split && k0 >= k_split;
+        // A: one 128-row box
+        tma_load_2d_elect(st, second ? &g.tm_a2 : &g.tm_a, second ? k0 - k_split : k0, um0, bar);
+        if (b_one) {
+          const bool hi = un0 >= n_split;
+          tma_load_2d_elect(st + 2 * U_TILE_BYTES, hi ? &g.tm_b2 : &g.tm_b, k0, hi ? un0 - n_split : un0, bar);
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) tma_load_2d_elect(st + j * 4096, ma, ka, um0 + 32 * j, bar);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = un0 + 32 * j;
-        const bool hi = r >= n_split;
-        tma_load_2d_elect(st + 2 * U_TILE_BYTES + j * 4096, hi ? &g.tm_b2 : &g.tm_b, k0, hi ? r - n_split : r, bar);
+          for (int j = 0; j < 4; ++j) {
+            const int r = un0 + 32 * j;
+            const bool hi = r >= n_split;
+            tma_load_2d_elect(st + 2 * U_TILE_BYTES + j * 4096, hi ? &g.tm_b2 : &g.tm_b, k0, hi ? r - n_split : r, bar);
+          }
+        }
       }
-    };
-    const int npre = nk < USTAGES ? nk : USTAGES;
-    long long c0 = dbg ? clk() : 0;
-    for (int s = 0; s < npre; ++s) issue_tma(s);
-    if (dbg && lane == 0) { const long long c1 = clk(); dbg[2] += c1 - c0; }
+      if (dbg && lane == 0) dbg[2] += clk() - c0;
+      __syncwarp();
+      return;
+    }
+    const uint32_t utmem = __shfl_sync(ub, tmem, 0);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
     for (int kt = 0; kt < nk; ++kt) {
       const uint32_t KT = kbase + (uint32_t)kt, GI = gbase + (uint32_t)(kt / UGROUP);
       const uint32_t stage = KT % USTAGES, b = GI & 1u;
-      c0 = dbg ? clk() : 0;
+      const long long c0 = dbg ? clk() : 0;
       if (kt % UGROUP == 0 && GI >= 2) u_mbar_wait(&bars.acc_empty[b], ((GI >> 1) - 1u) & 1u);
       u_mbar_wait(&bars.full[stage], (KT / USTAGES) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -650,10 +661,7 @@ __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const Ge
       u_mma_stage_elect(smem_base, stage * U_STAGE_BYTES, utmem + b * (uint32_t)UN, kt % UGROUP == 0, idesc);
       u_commit_elect(&bars.empty[stage]);
       if (kt % UGROUP == UGROUP - 1 || kt == nk - 1) u_commit_elect(&bars.acc_full[b]);
-      const long long c2 = dbg ? clk() : 0;
-      // refill the stage of the PREVIOUS k-tile (its MMAs finish while the ones just queued run)
-      if (kt >= 1 && kt - 1 + USTAGES < nk) issue_tma(kt - 1 + USTAGES);
-      if (dbg && lane == 0) { const long long c3 = clk(); dbg[0] += c1 - c0; dbg[1] += c2 - c1; dbg[2] += c3 - c2; }
+      if (dbg && lane == 0) { const long long c2 = clk(); dbg[0] += c1 - c0; dbg[1] += c2 - c1; }
     }
     __syncwarp();
     return;
@@ -1008,7 +1016,9 @@ __global__ void __launch_bounds__(kThreads, 1) tile_pipeline_kernel(const __grid
   }
   __syncthreads();
   StreamSmem sm{smem, P.slot_bytes, P.chunk_bytes, P.p};
-  if (tid >= U_PRODUCERS) {
+  if (tid >= U_PRODUCERS + 32) {
+    // (warp 9 has no job in the stream role)
+  } else if (tid >= U_PRODUCERS) {
     stream_loader(P, sm, s_meta, s_full, s_empty, st_cycles, tid & 31);
   } else {
     stream_workers(P, sm, s_meta, s_full, s_empty, tid, st_cycles);
@@ -1077,21 +1087,23 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   f.smem_bytes = sm + 1024;
   // tile: ~25 MB of resident feature map (both modalities), at least ~4 tiles for the pipeline, <= 128 samples
   const size_t per_sample = (size_t)2 * c * hw * 4;
-  long m = g_tile_m > 0 ? g_tile_m : (long)((25u << 20) / per_sample);
+  // tile: up to 128 samples (a full MMA), at least ~4 tiles for the pipeline
+  long m = g_tile_m > 0 ? g_tile_m : UM;
   if (m > UM) m = UM;
-  if (g_tile_m <= 0 && m > 8) m &= ~7L;
   if (g_tile_m <= 0 && m > (n + 3) / 4) m = (n + 3) / 4;
+  if (g_tile_m <= 0 && m > 8) m &= ~7L;
   if (m < 1) m = 1;
   f.m_tile = (int)m;
   f.n_tiles = (n + f.m_tile - 1) / f.m_tile;
-  f.lag = g_tile_lag < 1 ? 1 : g_tile_lag;
+  f.lag = g_tile_lag > 0 ? g_tile_lag : 6;
+  if (f.lag > f.n_tiles) f.lag = f.n_tiles;
   // GEMM stages: forward (K = 2C -> N = D), (K = D -> N = 2C); backward (K = 2C -> N = D), (K = D -> N = 2C)
   const int kk[2] = {2 * c, d}, nn[2] = {d, 2 * c};
   size_t items = 0, units = 0;
   for (int s = 0; s < 2; ++s) {
     f.nt[s] = ceil_div(nn[s], UN);
     const int nk = ceil_div(kk[s], UK);
-    int sp = ceil_div(nk, 8);
+    int sp = g_tile_ksplit_tiles > 0 ? ceil_div(nk, g_tile_ksplit_tiles) : 1;
     if (sp > kMaxSplits) sp = kMaxSplits;
     f.kps[s] = ceil_div(nk, sp) * UK;
     f.splits[s] = ceil_div(kk[s], f.kps[s]);
@@ -1104,8 +1116,11 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   // GEMM CTAs: k-tile units of one tile x ~0.6 us each, against the tile's streaming time at ~6.5 TB/s
   int g = g_tile_gemm_ctas;
   if (g <= 0) {
-    const double step_us = (double)f.m_tile * per_sample * (bwd ? 3.0 : 2.0) / 6.5e6;
-    g = (int)(units * 0.6 / (step_us > 0.1 ? step_us : 0.1)) + 2;
+    // GEMM-CTA cycles of one tile against the tile's streaming time (6u forward / 8u backward at ~5.5 TB/s, 1.9 GHz),
+    // with 2x head room: a tile's chain of FC items must also finish within the pipeline depth
+    const double step_cyc = (double)f.m_tile * per_sample * (bwd ? 4.0 : 3.0) / 5.5e12 * 1.9e9;
+    const double work_cyc = (double)units * 2200.0 + (double)items * 16000.0;  // measured per k-tile / per item (B200)
+    g = (int)(2.0 * work_cyc / (step_cyc > 1.0 ? step_cyc : 1.0)) + 2;
     if (g > 56) g = 56;
   }
   const int sms = sm_count();
@@ -1134,12 +1149,12 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 // fp32 [rows, k] with leading dimension ld (elements): box 32 k x 32 rows, 128-byte swizzle, zeros out of range
-int make_map(CUtensorMap* m, const float* base, int rows, int k, int ld) {
+int make_map(CUtensorMap* m, const float* base, int rows, int k, int ld, int box_rows) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return GML_E_UNSUPPORTED;
   const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)UK, 32u};
+  const cuuint32_t box[2] = {(cuuint32_t)UK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1161,6 +1176,7 @@ void fill_common(TileParams& P, const TileCfg& f, int n, int c, int hw, int d, b
   for (int s = 0; s < 2; ++s) {
     P.st[s].n_tiles = f.nt[s]; P.st[s].splits = f.splits[s]; P.st[s].k_per_split = f.kps[s];
     P.st[s].k_split = 0;
+    P.st[s].b_box_rows = 128;
     P.st[s].out2 = nullptr; P.st[s].bias = nullptr; P.st[s].bias2 = nullptr; P.st[s].mask = nullptr; P.st[s].ldmask = 0;
     P.st[s].div = 1.f;
   }
@@ -1205,10 +1221,15 @@ bool tile_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mode
   return make_tile_cfg(n, c_v, hw_v, d, false, &f) && make_tile_cfg(n, c_v, hw_v, d, true, &f);
 }
 
+// Automatic selection (measured on B200, profiles/r2_sweep.md): the pipeline streams at ~6 TB/s of real traffic but its S
+// stage re-reads from HBM (the FC chain of a tile takes longer than L2 can hold the tile), i.e. it moves 6u / 8u.  That
+// beats the streaming multi-kernel path and the cluster kernels' per-group weight re-reads for the weight-heavy blocks
+// (C >= 256) once the batch is large; the 128-channel block stays on the cluster kernels (4u / 6u from L2-resident groups).
 bool tile_preferred(int n, int c, int hw, int d) {
-  (void)d;
   if (g_tile_kind == 1) return true;
-  return (size_t)n * c * hw * 4 >= ((size_t)g_tile_min_mb << 20);
+  const size_t u = (size_t)n * c * hw * 4;
+  const size_t w_bytes = (size_t)16 * c * d;
+  return w_bytes >= (1u << 20) && u >= ((size_t)g_tile_min_mb << 20);
 }
 
 size_t tile_fwd_workspace_bytes(int n, int c, int hw, int d) {
@@ -1239,18 +1260,19 @@ int launch_tile_fwd(const FusedFwdArgs& a, float* gate_sum, float* run_v, float*
   P.add[0] = P.add[1] = nullptr;
   P.rout[0] = a.z; P.rout[1] = a.z + a.c; P.rout_ld = 2 * a.c;
   P.gate_scale = a.gate_scale;
+  const int bbox = a.c % 128 == 0 ? 128 : 32;  // B tiles of stage 1 must not straddle the W_v / W_s boundary
   GemmStage& s0 = P.st[0];   // H = relu(Z Wsq^T + bsq)
-  GML_TRY(make_map(&s0.tm_a, a.z, a.n, 2 * a.c, 2 * a.c));
-  GML_TRY(make_map(&s0.tm_b, a.w_sq, a.d, 2 * a.c, 2 * a.c));
+  GML_TRY(make_map(&s0.tm_a, a.z, a.n, 2 * a.c, 2 * a.c, 128));
+  GML_TRY(make_map(&s0.tm_b, a.w_sq, a.d, 2 * a.c, 2 * a.c, 128));
   s0.tm_a2 = s0.tm_a; s0.tm_b2 = s0.tm_b;
   s0.n_split = a.d; s0.n_total = a.d; s0.k_total = 2 * a.c;
   s0.out = a.h; s0.ldo = a.d; s0.bias = a.b_sq; s0.epi = kEpiRelu;
   GemmStage& s1 = P.st[1];   // [g_a | g_b] = sigmoid(H [Wv ; Ws]^T + [bv | bs])
-  GML_TRY(make_map(&s1.tm_a, a.h, a.n, a.d, a.d));
-  GML_TRY(make_map(&s1.tm_b, a.w_v, a.c, a.d, a.d));
-  GML_TRY(make_map(&s1.tm_b2, a.w_s, a.c, a.d, a.d));
+  GML_TRY(make_map(&s1.tm_a, a.h, a.n, a.d, a.d, 128));
+  GML_TRY(make_map(&s1.tm_b, a.w_v, a.c, a.d, a.d, bbox));
+  GML_TRY(make_map(&s1.tm_b2, a.w_s, a.c, a.d, a.d, bbox));
   s1.tm_a2 = s1.tm_a;
-  s1.n_split = a.c; s1.n_total = 2 * a.c;
+  s1.n_split = a.c; s1.n_total = 2 * a.c; s1.b_box_rows = bbox;
   s1.k_total = a.d; s1.out = a.g_a; s1.out2 = a.g_b; s1.ldo = a.c; s1.bias = a.b_v; s1.bias2 = a.b_s; s1.epi = kEpiSigmoid;
   if (gate_sum) {
     P.cs[0] = ColItem{a.g_a, gate_sum, a.n, a.c, a.c, run_v, run_s, (float)a.n, step};
@@ -1283,20 +1305,21 @@ int launch_tile_bwd(const FusedBwdArgs& a, float* dz_flat, float* d_b_v, float* 
   P.add[0] = dz_a; P.add[1] = dz_b;
   P.rout[0] = a.de_a; P.rout[1] = a.de_b; P.rout_ld = a.c;
   P.gate_scale = a.gate_scale;
+  const int bbox = a.c % 128 == 0 ? 128 : 32;
   GemmStage& s0 = P.st[0];   // dH = ([dE_a | dE_b] [Wv ; Ws]) * [H > 0]
-  GML_TRY(make_map(&s0.tm_a, a.de_a, a.n, a.c, a.c));
-  GML_TRY(make_map(&s0.tm_a2, a.de_b, a.n, a.c, a.c));
-  GML_TRY(make_map(&s0.tm_b, P.w_cat_t, a.d, 2 * a.c, 2 * a.c));
+  GML_TRY(make_map(&s0.tm_a, a.de_a, a.n, a.c, a.c, 128));
+  GML_TRY(make_map(&s0.tm_a2, a.de_b, a.n, a.c, a.c, 128));
+  GML_TRY(make_map(&s0.tm_b, P.w_cat_t, a.d, 2 * a.c, 2 * a.c, 128));
   s0.tm_b2 = s0.tm_b;
   s0.k_split = a.c; s0.n_split = a.d; s0.n_total = a.d; s0.k_total = 2 * a.c;
   s0.out = a.dh; s0.ldo = a.d; s0.mask = a.h; s0.ldmask = a.d; s0.epi = kEpiMask;
   GemmStage& s1 = P.st[1];   // dZ = dH Wsq, stored per modality and already divided by HW (MeanBackward)
   // (w_sq_t is ONE [2C, D] matrix: the second map simply continues it at row C, where the output switches to dz_b)
-  GML_TRY(make_map(&s1.tm_a, a.dh, a.n, a.d, a.d));
-  GML_TRY(make_map(&s1.tm_b, P.w_sq_t, a.c, a.d, a.d));
-  GML_TRY(make_map(&s1.tm_b2, P.w_sq_t + (size_t)a.c * a.d, a.c, a.d, a.d));
+  GML_TRY(make_map(&s1.tm_a, a.dh, a.n, a.d, a.d, 128));
+  GML_TRY(make_map(&s1.tm_b, P.w_sq_t, a.c, a.d, a.d, bbox));
+  GML_TRY(make_map(&s1.tm_b2, P.w_sq_t + (size_t)a.c * a.d, a.c, a.d, a.d, bbox));
   s1.tm_a2 = s1.tm_a;
-  s1.n_split = a.c; s1.n_total = 2 * a.c; s1.k_total = a.d; s1.out = dz_a; s1.out2 = dz_b; s1.ldo = a.c; s1.epi = kEpiDiv;
+  s1.n_split = a.c; s1.n_total = 2 * a.c; s1.b_box_rows = bbox; s1.k_total = a.d; s1.out = dz_a; s1.out2 = dz_b; s1.ldo = a.c; s1.epi = kEpiDiv;
   s1.div = (float)a.hw;
   int ncs = 0;
   if (d_b_v) P.cs[ncs++] = ColItem{a.de_a, d_b_v, a.n, a.c, a.c, nullptr, nullptr, 1.f, 0.f};

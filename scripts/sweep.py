@@ -39,6 +39,83 @@ VARIANTS = {
     "tile_g40": (L.F_FORCE_TILE, {"tile_gemm_ctas": 40}),
     "tile_c14": (L.F_FORCE_TILE, {"tile_chunk_kb": 14}),
     "tile_nodeps": (L.F_FORCE_TILE, {"tile_nodeps": 1, "tile_gemm_ctas": 8}),
+    "g_m4_l1": (L.F_FORCE_TILE, {"tile_m": 4, "tile_lag": 1, "tile_gemm_ctas": 8}),
+    "g_m4_l2": (L.F_FORCE_TILE, {"tile_m": 4, "tile_lag": 2, "tile_gemm_ctas": 8}),
+    "g_m4_l3": (L.F_FORCE_TILE, {"tile_m": 4, "tile_lag": 3, "tile_gemm_ctas": 8}),
+    "g_m4_l4": (L.F_FORCE_TILE, {"tile_m": 4, "tile_lag": 4, "tile_gemm_ctas": 8}),
+    "g_m4_l6": (L.F_FORCE_TILE, {"tile_m": 4, "tile_lag": 6, "tile_gemm_ctas": 8}),
+    "g_m8_l1": (L.F_FORCE_TILE, {"tile_m": 8, "tile_lag": 1, "tile_gemm_ctas": 8}),
+    "g_m8_l2": (L.F_FORCE_TILE, {"tile_m": 8, "tile_lag": 2, "tile_gemm_ctas": 8}),
+    "g_m8_l3": (L.F_FORCE_TILE, {"tile_m": 8, "tile_lag": 3, "tile_gemm_ctas": 8}),
+    "g_m8_l4": (L.F_FORCE_TILE, {"tile_m": 8, "tile_lag": 4, "tile_gemm_ctas": 8}),
+    "g_m8_l6": (L.F_FORCE_TILE, {"tile_m": 8, "tile_lag": 6, "tile_gemm_ctas": 8}),
+    "g_m16_l1": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 1, "tile_gemm_ctas": 8}),
+    "g_m16_l2": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 2, "tile_gemm_ctas": 8}),
+    "g_m16_l3": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 3, "tile_gemm_ctas": 8}),
+    "g_m16_l4": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 4, "tile_gemm_ctas": 8}),
+    "g_m16_l6": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 6, "tile_gemm_ctas": 8}),
+    "g_m32_l1": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 1, "tile_gemm_ctas": 8}),
+    "g_m32_l2": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 2, "tile_gemm_ctas": 8}),
+    "g_m32_l3": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 3, "tile_gemm_ctas": 8}),
+    "g_m32_l4": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 4, "tile_gemm_ctas": 8}),
+    "g_m32_l6": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 6, "tile_gemm_ctas": 8}),
+    "s_m64_l2_g12": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 2, "tile_gemm_ctas": 12}),
+    "s_m64_l2_g24": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 2, "tile_gemm_ctas": 24}),
+    "s_m64_l2_g40": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 2, "tile_gemm_ctas": 40}),
+    "s_m64_l2_g56": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 2, "tile_gemm_ctas": 56}),
+    "s_m64_l4_g12": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 4, "tile_gemm_ctas": 12}),
+    "s_m64_l4_g24": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 4, "tile_gemm_ctas": 24}),
+    "s_m64_l4_g40": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 4, "tile_gemm_ctas": 40}),
+    "s_m64_l4_g56": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 4, "tile_gemm_ctas": 56}),
+    "s_m64_l8_g12": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 8, "tile_gemm_ctas": 12}),
+    "s_m64_l8_g24": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 8, "tile_gemm_ctas": 24}),
+    "s_m64_l8_g40": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 8, "tile_gemm_ctas": 40}),
+    "s_m64_l8_g56": (L.F_FORCE_TILE, {"tile_m": 64, "tile_lag": 8, "tile_gemm_ctas": 56}),
+    "s_m128_l2_g12": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 2, "tile_gemm_ctas": 12}),
+    "s_m128_l2_g24": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 2, "tile_gemm_ctas": 24}),
+    "s_m128_l2_g40": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 2, "tile_gemm_ctas": 40}),
+    "s_m128_l2_g56": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 2, "tile_gemm_ctas": 56}),
+    "s_m128_l4_g12": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 4, "tile_gemm_ctas": 12}),
+    "s_m128_l4_g24": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 4, "tile_gemm_ctas": 24}),
+    "s_m128_l4_g40": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 4, "tile_gemm_ctas": 40}),
+    "s_m128_l4_g56": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 4, "tile_gemm_ctas": 56}),
+    "s_m128_l8_g12": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 8, "tile_gemm_ctas": 12}),
+    "s_m128_l8_g24": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 8, "tile_gemm_ctas": 24}),
+    "s_m128_l8_g40": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 8, "tile_gemm_ctas": 40}),
+    "s_m128_l8_g56": (L.F_FORCE_TILE, {"tile_m": 128, "tile_lag": 8, "tile_gemm_ctas": 56}),
+    "n_g8": (L.F_FORCE_TILE, {"tile_gemm_ctas": 8}),
+    "n_g12": (L.F_FORCE_TILE, {"tile_gemm_ctas": 12}),
+    "n_g16": (L.F_FORCE_TILE, {"tile_gemm_ctas": 16}),
+    "n_g24": (L.F_FORCE_TILE, {"tile_gemm_ctas": 24}),
+    "n_g32": (L.F_FORCE_TILE, {"tile_gemm_ctas": 32}),
+    "n_g40": (L.F_FORCE_TILE, {"tile_gemm_ctas": 40}),
+    "n_auto": (L.F_FORCE_TILE, {}),
+    "n_ks8_g24": (L.F_FORCE_TILE, {"tile_gemm_ctas": 24, "tile_ksplit_tiles": 8}),
+    "q_m12_l1": (L.F_FORCE_TILE, {"tile_m": 12, "tile_lag": 1, "tile_gemm_ctas": 6}),
+    "q_m12_l2": (L.F_FORCE_TILE, {"tile_m": 12, "tile_lag": 2, "tile_gemm_ctas": 6}),
+    "q_m12_l3": (L.F_FORCE_TILE, {"tile_m": 12, "tile_lag": 3, "tile_gemm_ctas": 6}),
+    "q_m16_l1": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 1, "tile_gemm_ctas": 6}),
+    "q_m16_l2": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 2, "tile_gemm_ctas": 6}),
+    "q_m16_l3": (L.F_FORCE_TILE, {"tile_m": 16, "tile_lag": 3, "tile_gemm_ctas": 6}),
+    "q_m20_l1": (L.F_FORCE_TILE, {"tile_m": 20, "tile_lag": 1, "tile_gemm_ctas": 6}),
+    "q_m20_l2": (L.F_FORCE_TILE, {"tile_m": 20, "tile_lag": 2, "tile_gemm_ctas": 6}),
+    "q_m20_l3": (L.F_FORCE_TILE, {"tile_m": 20, "tile_lag": 3, "tile_gemm_ctas": 6}),
+    "q_m24_l1": (L.F_FORCE_TILE, {"tile_m": 24, "tile_lag": 1, "tile_gemm_ctas": 6}),
+    "q_m24_l2": (L.F_FORCE_TILE, {"tile_m": 24, "tile_lag": 2, "tile_gemm_ctas": 6}),
+    "q_m24_l3": (L.F_FORCE_TILE, {"tile_m": 24, "tile_lag": 3, "tile_gemm_ctas": 6}),
+    "q_m28_l1": (L.F_FORCE_TILE, {"tile_m": 28, "tile_lag": 1, "tile_gemm_ctas": 6}),
+    "q_m28_l2": (L.F_FORCE_TILE, {"tile_m": 28, "tile_lag": 2, "tile_gemm_ctas": 6}),
+    "q_m28_l3": (L.F_FORCE_TILE, {"tile_m": 28, "tile_lag": 3, "tile_gemm_ctas": 6}),
+    "q_m32_l1": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 1, "tile_gemm_ctas": 6}),
+    "q_m32_l2": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 2, "tile_gemm_ctas": 6}),
+    "q_m32_l3": (L.F_FORCE_TILE, {"tile_m": 32, "tile_lag": 3, "tile_gemm_ctas": 6}),
+    "q_m40_l1": (L.F_FORCE_TILE, {"tile_m": 40, "tile_lag": 1, "tile_gemm_ctas": 6}),
+    "q_m40_l2": (L.F_FORCE_TILE, {"tile_m": 40, "tile_lag": 2, "tile_gemm_ctas": 6}),
+    "q_m40_l3": (L.F_FORCE_TILE, {"tile_m": 40, "tile_lag": 3, "tile_gemm_ctas": 6}),
+    "q_m48_l1": (L.F_FORCE_TILE, {"tile_m": 48, "tile_lag": 1, "tile_gemm_ctas": 6}),
+    "q_m48_l2": (L.F_FORCE_TILE, {"tile_m": 48, "tile_lag": 2, "tile_gemm_ctas": 6}),
+    "q_m48_l3": (L.F_FORCE_TILE, {"tile_m": 48, "tile_lag": 3, "tile_gemm_ctas": 6}),
+    "tile_nostore": (L.F_FORCE_TILE, {"tile_nodeps": 4, "tile_gemm_ctas": 8}),
     "tile_noop": (L.F_FORCE_TILE, {"tile_nodeps": 2, "tile_gemm_ctas": 8}),
     "tile_noop_c14": (L.F_FORCE_TILE, {"tile_nodeps": 2, "tile_gemm_ctas": 8, "tile_chunk_kb": 14}),
     "tile_noop_c50": (L.F_FORCE_TILE, {"tile_nodeps": 2, "tile_gemm_ctas": 8, "tile_chunk_kb": 50}),
@@ -123,7 +200,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 2, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 # workspace sizes depend on the tile tunables: re-query for this variant
                 b.ws_bytes = lib.gml_mmtm_bwd_workspace_bytes(b.dims)

@@ -26,20 +26,23 @@ SHAPES = [(1, 32, 4, 4), (2, 32, 7, 7), (4, 32, 1, 1), (3, 32, 5, 2), (33, 32, 3
 @pytest.fixture
 def tile_tunables(request):
     lib = _lib.load()
-    m, lag, gemm = request.param
+    m, lag, gemm, ksplit = request.param
     _lib.check(lib.gml_set_tunable(b"tile_m", m))
     _lib.check(lib.gml_set_tunable(b"tile_lag", lag))
     _lib.check(lib.gml_set_tunable(b"tile_gemm_ctas", gemm))
+    _lib.check(lib.gml_set_tunable(b"tile_ksplit_tiles", ksplit))
     yield request.param
     _lib.check(lib.gml_set_tunable(b"tile_m", 0))
-    _lib.check(lib.gml_set_tunable(b"tile_lag", 2))
+    _lib.check(lib.gml_set_tunable(b"tile_lag", 0))
     _lib.check(lib.gml_set_tunable(b"tile_gemm_ctas", 0))
+    _lib.check(lib.gml_set_tunable(b"tile_ksplit_tiles", 0))
 
 
-# (samples per tile, lag, GEMM CTAs): automatic; tiny tiles (many tiles -> dependency counters, partial-plane ring
-# reuse) with a deep and a shallow pipeline; a single GEMM CTA (every F item serialised behind its dependencies)
-@pytest.mark.parametrize("tile_tunables", [(0, 2, 0), (2, 1, 3), (3, 4, 1)], indirect=True,
-                         ids=["auto", "m2_lag1_g3", "m3_lag4_g1"])
+# (samples per tile, lag, GEMM CTAs, k-tiles per split-K item): automatic; tiny tiles (many tiles -> dependency
+# counters, partial-plane ring reuse) with a shallow pipeline and split-K (partials folded in split order by the last
+# split to finish); a deep pipeline with a single GEMM CTA (every F item serialised behind its dependencies)
+@pytest.mark.parametrize("tile_tunables", [(0, 0, 0, 0), (2, 1, 3, 4), (3, 4, 1, 0), (0, 2, 0, 2)], indirect=True,
+                         ids=["auto", "m2_lag1_g3_ks4", "m3_lag4_g1", "auto_lag2_ks2"])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "n%dc%d_%dx%d" % s)
 def test_tile_pipeline_vs_oracle(shape, tile_tunables):
     n, c, h, w = shape
