@@ -43,10 +43,13 @@ __device__ __forceinline__ double block_sum_to_double(float v, float* smem) {
 __global__ void __launch_bounds__(kSqThreads)
     sqnorm_kernel(const __grid_constant__ SqnormTable tab, double* __restrict__ partial, unsigned int* counter,
                   double* __restrict__ out8, double* __restrict__ per_tensor, int accumulate_out) {
-  __shared__ float red[kSqThreads / 32];
   __shared__ bool is_last;
+  // One WARP per chunk, no block barrier in the scan: 64 warps per SM with 8 independent 128-bit loads per lane keep
+  // ~256 KB in flight per SM, enough to cover HBM latency at full bandwidth.
   const int n_chunks = tab.chunk_start[tab.n_tensors];
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * (kSqThreads / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (kSqThreads / 32);
+  for (int chunk = gwarp; chunk < n_chunks; chunk += nwarps) {
     // binary search: largest t with chunk_start[t] <= chunk
     int lo = 0, hi = tab.n_tensors;
     while (hi - lo > 1) {
@@ -61,29 +64,32 @@ __global__ void __launch_bounds__(kSqThreads)
     if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
       const float4* p4 = reinterpret_cast<const float4*>(p);
       const int n4 = cnt >> 2;
-      float4 v[4];
+      for (int j0 = lane; j0 < n4; j0 += 8 * 32) {
+        float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = threadIdx.x + u * kSqThreads;
-        v[u] = j < n4 ? ldg_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + u * 32;
+          v[u] = j < n4 ? ldg_stream(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a0 = fmaf(v[u].x, v[u].x, a0); a1 = fmaf(v[u].y, v[u].y, a1);
-        a2 = fmaf(v[u].z, v[u].z, a2); a3 = fmaf(v[u].w, v[u].w, a3);
+        for (int u = 0; u < 8; ++u) {
+          a0 = fmaf(v[u].x, v[u].x, a0); a1 = fmaf(v[u].y, v[u].y, a1);
+          a2 = fmaf(v[u].z, v[u].z, a2); a3 = fmaf(v[u].w, v[u].w, a3);
+        }
       }
-      for (int j = (n4 << 2) + threadIdx.x; j < cnt; j += kSqThreads) a0 = fmaf(p[j], p[j], a0);
+      for (int j = (n4 << 2) + lane; j < cnt; j += 32) a0 = fmaf(p[j], p[j], a0);
     } else {
-      for (int j = threadIdx.x; j < cnt; j += kSqThreads) {
+      for (int j = lane; j < cnt; j += 32) {
         const float x = __ldg(p + j);
         a0 = fmaf(x, x, a0);
       }
     }
-    const double s = block_sum_to_double((a0 + a1) + (a2 + a3), red);
-    if (threadIdx.x == 0) partial[chunk] = s;
+    const float s = warp_sum((a0 + a1) + (a2 + a3));  // fp32 inside the chunk, fixed shuffle tree
+    if (lane == 0) partial[chunk] = (double)s;
   }
   // last block to finish folds the partials in a fixed order
   __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int done = atomicAdd(counter, 1u);
     is_last = (done == gridDim.x - 1);
@@ -91,12 +97,28 @@ __global__ void __launch_bounds__(kSqThreads)
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // one warp per tensor: lane l adds chunks l, l + 32, ... (four loads in flight), then a fixed shuffle tree --
+  // a fixed order, so the result is bit-reproducible; the big convolution weights have ~600 chunks each and a
+  // single thread walking them was the tail of the whole launch
   __shared__ double tsum[kMaxTensors];
-  for (int t = threadIdx.x; t < tab.n_tensors; t += kSqThreads) {
-    double s = 0.0;
-    for (int c = tab.chunk_start[t]; c < tab.chunk_start[t + 1]; ++c) s += __ldcg(partial + c);
-    tsum[t] = s;
-    if (per_tensor) per_tensor[t] = s;
+  const int warp = threadIdx.x >> 5;
+  for (int t = warp; t < tab.n_tensors; t += kSqThreads / 32) {
+    const int c0 = tab.chunk_start[t], c1 = tab.chunk_start[t + 1];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = c0 + lane;
+    for (; c + 96 < c1; c += 128) {
+      const double v0 = __ldcg(partial + c), v1 = __ldcg(partial + c + 32), v2 = __ldcg(partial + c + 64),
+                   v3 = __ldcg(partial + c + 96);
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    }
+    for (; c < c1; c += 32) s0 += __ldcg(partial + c);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      tsum[t] = s;
+      if (per_tensor) per_tensor[t] = s;
+    }
   }
   __syncthreads();
   if (threadIdx.x < 8) {

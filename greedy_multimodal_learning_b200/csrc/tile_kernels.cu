@@ -1116,11 +1116,11 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   // GEMM CTAs: k-tile units of one tile x ~0.6 us each, against the tile's streaming time at ~6.5 TB/s
   int g = g_tile_gemm_ctas;
   if (g <= 0) {
-    // GEMM-CTA cycles of one tile against the tile's streaming time (6u forward / 8u backward at ~5.5 TB/s, 1.9 GHz),
-    // with 2x head room: a tile's chain of FC items must also finish within the pipeline depth
-    const double step_cyc = (double)f.m_tile * per_sample * (bwd ? 4.0 : 3.0) / 5.5e12 * 1.9e9;
-    const double work_cyc = (double)units * 2200.0 + (double)items * 16000.0;  // measured per k-tile / per item (B200)
-    g = (int)(2.0 * work_cyc / (step_cyc > 1.0 ? step_cyc : 1.0)) + 2;
+    // The 3xTF32 FC work of a tile grows with C^2 while its bytes grow with C: measured best on B200 (profiles/
+    // r2_sweep.md) 48 CTAs for C = 512, 12 for 256, 3-4 for 128 -- i.e. ~C*D/5500 -- in both directions.
+    (void)units; (void)items;
+    g = (int)((double)c * d / 5461.0 + 0.5);
+    if (g < 3) g = 3;
     if (g > 56) g = 56;
   }
   const int sms = sm_count();
