@@ -176,29 +176,28 @@ class Bias_Mitigation_Strong(Callback):
         logs['d_BDR'] = self.d_BDR
 
     def on_backward_end(self, batch):
+        """Decision for the NEXT step (it runs before optimizer.step, src/framework.py:313-315):
+        locked -> keep accumulating the statistic, normal mode; unlocked and normal -> measure and, when the two
+        conditional learning speeds differ by more than epsilon, open a window that cares for the slower modality;
+        inside a window -> count steps only (the statistic is neither measured nor accumulated there)."""
         mp = self.model_pytoune
-        if self.unlock:
-            if not mp.curation_mode:
-                self.d_BDR = self.compute_BDR()
-                if abs(self.d_BDR) > self.epsilon:
-                    biased_direction = np.sign(self.d_BDR)
-                    mp.curation_mode = True
-                    self.curation_step = 0
-                    if biased_direction == -1:    # BDR0 < BDR1
-                        mp.caring_modality = 1
-                    elif biased_direction == 1:   # BDR0 > BDR1
-                        mp.caring_modality = 0
-                else:
-                    mp.curation_mode = False
-                    mp.caring_modality = 0
-            else:
-                # inside a window the statistic is neither computed nor accumulated
-                self.curation_step += 1
-                if self.curation_step == self.curation_windowsize:
-                    mp.curation_mode = False
+        if self.unlock and mp.curation_mode:
+            self.curation_step += 1
+            if self.curation_step == self.curation_windowsize:
+                mp.curation_mode = False
+            return
+        self.d_BDR = self.compute_BDR()
+        imbalanced = self.unlock and abs(self.d_BDR) > self.epsilon
+        mp.curation_mode = bool(imbalanced)
+        if imbalanced:
+            self.curation_step = 0
+            direction = np.sign(self.d_BDR)
+            if direction > 0:
+                mp.caring_modality = 0
+            elif direction < 0:
+                mp.caring_modality = 1
+            # (a NaN statistic leaves caring_modality as it was, like the reference's two-way branch)
         else:
-            self.d_BDR = self.compute_BDR()
-            mp.curation_mode = False
             mp.caring_modality = 0
 
     def on_epoch_begin(self, epoch, logs):

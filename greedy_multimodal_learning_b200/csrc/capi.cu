@@ -366,6 +366,7 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
   const bool curate = mode == GML_MODE_CURATE_VISUAL || mode == GML_MODE_CURATE_SKELETON;
   if (curate && (!run_v || !run_s)) return GML_E_BADARG;
   if (d.n == 0) return GML_OK;
+  if (workspace && workspace_bytes < gemm_workspace_bytes()) return GML_E_WORKSPACE;  // NULL = no split-K, always fine
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   const bool can_tile = !(flags & (GML_F_FORCE_STREAMING | GML_F_FORCE_FUSED)) && !curate && workspace &&
@@ -386,10 +387,14 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
   if (can_fuse && ((flags & GML_F_FORCE_FUSED) || fused_fwd_preferred(d.n, d.c_v, d.hw_v, d.d))) {
     FusedFwdArgs fa{a, b, a_out, b_out, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, run_v, run_s,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
-    GML_TRY(launch_fused_fwd(fa, st));
-    ColsumSeg cs{g_a, gate_sum, d.n, d.c_v, d.c_v, update ? run_v : nullptr, update ? run_s : nullptr, (float)d.n,
-                 (float)step};
-    return launch_colsums(&cs, 1, st);
+    const int rc = launch_fused_fwd(fa, st);
+    if (rc == GML_OK) {
+      ColsumSeg cs{g_a, gate_sum, d.n, d.c_v, d.c_v, update ? run_v : nullptr, update ? run_s : nullptr, (float)d.n,
+                   (float)step};
+      return launch_colsums(&cs, 1, st);
+    }
+    // misaligned pointers: the streaming path below takes any 4-byte alignment
+    if (rc != GML_E_UNSUPPORTED || (flags & GML_F_FORCE_FUSED)) return rc;
   }
 
   GML_TRY(prepare_gemm_workspace(workspace, workspace_bytes, st));
@@ -508,7 +513,7 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   const bool can_tile = !(flags & (GML_F_FORCE_STREAMING | GML_F_FORCE_FUSED)) && la && lb && tile_bytes &&
                         tile_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
   if ((flags & GML_F_FORCE_TILE) && !can_tile) return GML_E_UNSUPPORTED;
-  bool tiled = false;
+  bool tiled = false, fused_done = false;
   if (can_tile && ((flags & GML_F_FORCE_TILE) || tile_preferred(d.n, d.c_v, d.hw_v, d.d))) {
     FusedBwdArgs fb{go_a, go_b, a, b, w_sq, w_v, w_s, z, h, g_a, g_b, run_v, run_s, d_a, d_b, de_a, de_b, dh,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
@@ -525,8 +530,11 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   } else if (can_fuse) {
     FusedBwdArgs fb{go_a, go_b, a, b, w_sq, w_v, w_s, z, h, g_a, g_b, run_v, run_s, d_a, d_b, de_a, de_b, dh,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
-    GML_TRY(launch_fused_bwd(fb, st));
-  } else {
+    const int rc = launch_fused_bwd(fb, st);
+    if (rc != GML_OK && (rc != GML_E_UNSUPPORTED || (flags & GML_F_FORCE_FUSED))) return rc;
+    fused_done = rc == GML_OK;
+  }
+  if (!tiled && !fused_done) {
     // grad_out is read twice (dot, then apply): keep it in L2 per chunk.  a/b stream through once.
     const size_t per_sample = ((size_t)d.c_v * d.hw_v + (size_t)d.c_s * d.hw_s) * sizeof(float);
     const int cs = chunk_samples(d, per_sample);

@@ -234,7 +234,11 @@ class Model_:
         self.curation_mode = False
         self.caring_modality = None
         self.data_parallel = data_parallel
-        self._fast_acc = len(metrics) == 1 and metrics[0] is acc
+        # device-side counts recompute the fused prediction as (l0 + l1) / 2 (src/model.py:108): only valid for models
+        # that say so (`fused_logits_are_view_mean`, set by MMTM_MVCNN); anything else takes the generic path
+        self._fast_acc = (len(metrics) == 1 and metrics[0] is acc and
+                          bool(getattr(model, "fused_logits_are_view_mean", False)))
+        self.last_correct_counts = None
         self._stat_dev = None
 
     # -- device plumbing ------------------------------------------------------------------
@@ -305,7 +309,7 @@ class Model_:
         with torch.no_grad():
             if self._fast_acc and self.nummodalities == 2 and loss.is_cuda:
                 counts = self._launch_counts(pred_y, y)
-                step['loss'], step['metrics'], step['viewwises_metrics'], step['correct_counts'] = \
+                step['loss'], step['metrics'], step['viewwises_metrics'], self.last_correct_counts = \
                     self._read_back(loss, counts, n)
             else:
                 step['metrics'], step['viewwises_metrics'] = self._generic_metrics(pred_eval, pred_y, y)

@@ -46,6 +46,8 @@ class MMTM_MVCNN(nn.Module):
         self.mmtm3 = mmtm_cls(*MMTM_DIMS[1])
         self.mmtm4 = mmtm_cls(*MMTM_DIMS[2])
 
+    fused_logits_are_view_mean = True  # forward returns (x_0 + x_1) / 2: lets the step engine count on the device
+
     def mmtm_blocks(self):
         return [self.mmtm2, self.mmtm3, self.mmtm4]
 

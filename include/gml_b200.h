@@ -11,9 +11,14 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is DEVICE memory unless the name ends in
  *     `_host`.  The caller owns all buffers (PyTorch caching allocator in practice); the
- *     library allocates nothing persistent and keeps no state between calls.
+ *     library allocates no device memory and keeps no DATA state between calls.  What it does
+ *     keep, per process: the tunables of gml_set_tunable (plain process-wide settings: set
+ *     them before launching work, not concurrently with it), the launch counters, one lazily
+ *     created helper stream + two events per host thread and device, and cached
+ *     occupancy / function-attribute queries (mutex-protected).
  *   - every call is asynchronous and stream-ordered on `stream` (a cudaStream_t passed as
- *     void*; NULL = legacy default stream).  Re-entrant and thread-safe.
+ *     void*; NULL = legacy default stream).  Calls from several host threads are safe as long
+ *     as nobody changes a tunable meanwhile.
  *   - return value: 0 on success, a negative GML_E_* code otherwise; never throws.
  *   - tensors are fp32, dense, row-major.  Feature maps are NCHW-contiguous, seen as
  *     [N, C, HW] (the reference's `.view(shape[:2] + (-1,))`, src/balanced_mmtm.py:96).
@@ -170,8 +175,9 @@ int gml_mmtm_apply(const float* a, const float* b, float* a_out, float* b_out,
  *   dWv  = dE_a^T H, dbv = sum_n dE_a, dWs = dE_b^T H, dbs = sum_n dE_b,
  *   dWsq = dH^T Z, dbsq = sum_rows dH
  * Weight gradients are OVERWRITTEN (the caller's autograd accumulates).  On a substituted
- * side (curation) the excitation FC receives no gradient: its dW/db are zero-filled and
- * *_has_grad reports it (the reference leaves .grad = None there).
+ * side (curation) the excitation FC receives no gradient: its dW/db, if requested, are
+ * zero-filled (the reference leaves .grad = None there; the Python mirror passes NULL and
+ * returns None for them).
  * run_v/run_s are the values the forward USED (pass a saved copy).  d_a/d_b must not alias
  * grad_a_out/grad_b_out.  Any of the six weight-gradient pointers may be NULL to skip it.
  * z, h, g_a, g_b are the buffers the forward of the SAME mode produced.
