@@ -19,10 +19,10 @@ Prints ONE JSON line (rank 0):
   cpu_baseline  the reference's own `MMTM_mitigate` (unmodified, from the git-ignored mirror baseline/_ref;
              the oracle port where the mirror is absent) on the host cores: a bounded sample of the same
              workload at the SAME batch, all host threads
-  train      guided 2-view training step end to end (cuDNN backbone + CUDA MMTM + one-launch
+  train      guided 2-view training step end to end (cuDNN backbone + CUDA MMTM + one-call
              learning-speed statistic), samples/s, next to the CPU reference-path step
 
-  stats      K4: the one-launch learning-speed reduction over the real model's 142 parameters + gradients
+  stats      K4: the one-call (two-launch) learning-speed reduction over the real model's 142 parameters + gradients
              (190 MB), device time / GB/s, next to the reference's per-tensor loop on the host
   dp_parity  (N > 1) one block computed batch-sharded over the ranks vs rank 0's oracle on the whole batch
 
@@ -538,7 +538,8 @@ def run_ours(args):
 
 def bench_stats(torch, pkg, L, lib, dev, peak, with_cpu):
     """K4: sum of squares of the 142 parameters and 142 gradients of MMTM_MVCNN (2 x 23,773,008 fp32 =
-    190.2 MB) in one launch; device time from CUDA events around the C-ABI call, L2 flushed before each call.  The
+    190.2 MB) in one call = a scan launch + a one-cluster fold launch (programmatic dependent launch); device time from
+    CUDA events around the C-ABI call, L2 flushed before each call.  The
     reference's loop (src/callbacks.py:203-205: two reductions + two .item() per tensor) is timed on the host beside it."""
     BR, MM = ["net_view_0", "net_view_1"], ["visual", "skeleton"]
     torch.manual_seed(777)
@@ -570,8 +571,10 @@ def bench_stats(torch, pkg, L, lib, dev, peak, with_cpu):
     ms = statistics.median(times)
     out = {"tensors": nt, "algorithmic_bytes": nbytes, "device_ms": ms, "gbs": nbytes / (ms * 1e-3) / 1e9,
            "frac_of_measured_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak, "call_ms_incl_readback": full_ms,
-           "note": "gml_multi_tensor_sqnorm over MMTM_MVCNN (src/callbacks.py:203-223), cold L2; device_ms includes the "
-                   "4-byte counter memset"}
+           "launches_per_call": 2,
+           "note": "gml_multi_tensor_sqnorm over MMTM_MVCNN (src/callbacks.py:203-223), cold L2; device_ms spans both "
+                   "launches (scan over all tensors, then a one-cluster fold); profiles/r2_sqnorm.md has the per-kernel "
+                   "ncu times (scan alone 32.9 us = 0.88 of the measured HBM peak)"}
     if with_cpu:
         from oracle import stats_oracle as so
         cpu_named = [(n_, p_.detach().cpu(), p_.grad.cpu()) for n_, p_ in model.named_parameters()]

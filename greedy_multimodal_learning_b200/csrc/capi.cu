@@ -250,6 +250,7 @@ extern long long* g_gemm_trace;
 extern int g_fused_weight_ratio_x100;
 extern int g_fused_group_kb;
 extern int g_fused_stash_kb;
+extern int g_sq_variant;
 extern int g_tile_kind, g_tile_lag, g_tile_gemm_ctas, g_tile_m, g_tile_chunk_kb, g_tile_min_mb;
 extern long long* g_tile_stats;
 extern int g_tile_nodeps, g_tile_ksplit_tiles;
@@ -290,6 +291,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "tile_ksplit_tiles")) { g_tile_ksplit_tiles = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "tile_nodeps")) { g_tile_nodeps = (int)value; return GML_OK; }
   if (!strcmp(name, "tile_stats_ptr")) { g_tile_stats = reinterpret_cast<long long*>(value); return GML_OK; }
+  if (!strcmp(name, "sq_variant")) { g_sq_variant = (int)value & 127; return GML_OK; }
   if (!strcmp(name, "tile_min_mb")) { g_tile_min_mb = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "fused_threads")) {
     if (value != 0 && value != 256 && value != 512) return GML_E_BADARG;

@@ -7,14 +7,20 @@
 //   * argmax/equality accuracy counts (train.py:32-40).
 // All three are HBM-bound scans; no tensor cores, no atomics on the data path, fixed reduction
 // order (bit-reproducible).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace gml {
 
+// tunable "sq_variant" (measurement): bits 0-1 chunk {4096, 2048, 1024, 8192} elements, bit 2 = no programmatic
+// dependent launch of the fold, bits 3-6 blocks per SM (0 = 8)
+int g_sq_variant = 0;
+
 namespace {
 
 constexpr int kMaxTensors = 1024;  // per launch; 14.3 KB of kernel parameters (CUDA >= 12.1 allows 32 KB)
-constexpr int kChunk = 4096;       // elements per chunk = 256 threads x 4 x float4
+constexpr int kMinChunk = 1024;    // smallest chunk (elements) a variant may use: sizes the workspace
 constexpr int kSqThreads = 256;
 
 struct SqnormTable {
@@ -40,12 +46,21 @@ __device__ __forceinline__ double block_sum_to_double(float v, float* smem) {
   return r;  // valid in thread 0
 }
 
+// Reduction tree (fixed order at every level, so the result is bit-reproducible):
+//   chunk   : fp32 in the lane, fixed shuffle tree                               (scan kernel, one warp per chunk)
+//   tensor  : lane l adds chunks l, l + 32, ... in fp64, then a fixed shuffle tree (fold kernel, one warp per tensor)
+//   bucket  : lane l adds tensors l, l + 32, ... of the bucket, shuffle tree       (fold kernel, one warp per output)
+// Two launches, the second one a single 1024-thread block started with programmatic dependent launch so that its
+// launch latency hides behind the scan.  What was measured on the way here (profiles/r2_sqnorm.md):
+//   * one "last block" folding all tensors after the scan: the SMs were active 64 k of the launch's 132 k cycles;
+//   * per-tensor arrival counters (fold by the warp that completes a tensor): a fence + atomic round trip per
+//     chunk, 50 us under ncu, and the counters cost a memset launch per call;
+//   * ticket scheduling of chunks: slower than a static stride (one more round trip per chunk).
+template <int kChunk>
 __global__ void __launch_bounds__(kSqThreads)
-    sqnorm_kernel(const __grid_constant__ SqnormTable tab, double* __restrict__ partial, unsigned int* counter,
-                  double* __restrict__ out8, double* __restrict__ per_tensor, int accumulate_out) {
-  __shared__ bool is_last;
-  // One WARP per chunk, no block barrier in the scan: 64 warps per SM with 8 independent 128-bit loads per lane keep
-  // ~256 KB in flight per SM, enough to cover HBM latency at full bandwidth.
+    sqnorm_scan_kernel(const __grid_constant__ SqnormTable tab, double* __restrict__ partial) {
+  // One WARP per chunk, no block barrier: 8 independent 128-bit loads per lane.  The host sizes the grid so that
+  // every warp gets the same number of chunks (+-1): with ~1.2 chunks per warp a third of the launch was a tail.
   const int n_chunks = tab.chunk_start[tab.n_tensors];
   const int lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * (kSqThreads / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (kSqThreads / 32);
@@ -87,25 +102,44 @@ __global__ void __launch_bounds__(kSqThreads)
     const float s = warp_sum((a0 + a1) + (a2 + a3));  // fp32 inside the chunk, fixed shuffle tree
     if (lane == 0) partial[chunk] = (double)s;
   }
-  // last block to finish folds the partials in a fixed order
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int done = atomicAdd(counter, 1u);
-    is_last = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // one warp per tensor: lane l adds chunks l, l + 32, ... (four loads in flight), then a fixed shuffle tree --
-  // a fixed order, so the result is bit-reproducible; the big convolution weights have ~600 chunks each and a
-  // single thread walking them was the tail of the whole launch
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+constexpr int kFoldThreads = 1024;
+constexpr int kFoldCluster = 8;  // one cluster of 8 x 32 warps: every tensor of the real model gets its own warp
+
+__global__ void __launch_bounds__(kFoldThreads)
+    sqnorm_fold_kernel(const __grid_constant__ SqnormTable tab, const double* __restrict__ partial,
+                       double* __restrict__ out8, double* __restrict__ per_tensor, int accumulate_out) {
+  // A single block walking ~9 tensors per warp one after the other took 18 us (r2_sqnorm3.ncu-rep): each tensor is a
+  // chain of constant-bank misses, L2 loads and five fp64 shuffles.  A cluster gives 256 warps and a hardware barrier;
+  // the per-tensor sums and bucket codes travel to CTA 0 through distributed shared memory, so the last stage reads
+  // shared memory only (indexing the constant bank per lane would serialise).
+  namespace cg = cooperative_groups;
   __shared__ double tsum[kMaxTensors];
-  const int warp = threadIdx.x >> 5;
-  for (int t = warp; t < tab.n_tensors; t += kSqThreads / 32) {
+  __shared__ unsigned char code[kMaxTensors];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rank = (int)cluster.block_rank(), wpc = kFoldThreads / 32;
+  double* tsum0 = cluster.map_shared_rank(tsum, 0);
+  unsigned char* code0 = cluster.map_shared_rank(code, 0);
+  // arrive now, wait just before the first remote write: CTA 0 must be resident before anyone writes into its
+  // shared memory, but nobody has to wait for that while folding
+  auto token = cluster.barrier_arrive();
+  bool synced = false;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the scan's partials are complete and visible after this
+  for (int t = rank * wpc + warp; t < tab.n_tensors; t += (int)cluster.num_blocks() * wpc) {
     const int c0 = tab.chunk_start[t], c1 = tab.chunk_start[t + 1];
+    const unsigned char cd = (unsigned char)(tab.kind[t] * 16 + tab.mask[t]);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int c = c0 + lane;
+    for (; c + 224 < c1; c += 256) {  // eight loads in flight; the order of the additions does not depend on it
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + c + 32 * u);
+      s0 += v[0]; s1 += v[1]; s2 += v[2]; s3 += v[3];
+      s0 += v[4]; s1 += v[5]; s2 += v[6]; s3 += v[7];
+    }
     for (; c + 96 < c1; c += 128) {
       const double v0 = __ldcg(partial + c), v1 = __ldcg(partial + c + 32), v2 = __ldcg(partial + c + 64),
                    v3 = __ldcg(partial + c + 96);
@@ -115,21 +149,29 @@ __global__ void __launch_bounds__(kSqThreads)
     double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (!synced) {
+      cluster.barrier_wait(std::move(token));
+      synced = true;
+    }
     if (lane == 0) {
-      tsum[t] = s;
+      tsum0[t] = s;
+      code0[t] = cd;
       if (per_tensor) per_tensor[t] = s;
     }
   }
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    const int bit = 1 << (threadIdx.x & 3);
-    const int kind = threadIdx.x >> 2;
-    double s = accumulate_out ? out8[threadIdx.x] : 0.0;
-    for (int t = 0; t < tab.n_tensors; ++t)
-      if (tab.kind[t] == kind && (tab.mask[t] & bit)) s += tsum[t];
-    out8[threadIdx.x] = s;
+  if (!synced) cluster.barrier_wait(std::move(token));
+  cluster.sync();
+  if (rank == 0 && warp < 8) {  // out8 index: kind * 4 + bucket bit
+    const int bit = 1 << (warp & 3), kind = warp >> 2;
+    double s = 0.0;
+    for (int t = lane; t < tab.n_tensors; t += 32) {
+      const int cd = code[t];
+      if ((cd >> 4) == kind && (cd & bit)) s += tsum[t];
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
+    if (lane == 0) out8[warp] = (accumulate_out ? out8[warp] : 0.0) + s;
   }
-  if (threadIdx.x == 0) *counter = 0u;  // workspace is reusable without a memset
 }
 
 __global__ void __launch_bounds__(256)
@@ -177,7 +219,7 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x < 3) counts3[threadIdx.x] = cnt[threadIdx.x];
 }
 
-inline long long chunks_of(long long numel) { return (numel + kChunk - 1) / kChunk; }
+inline long long chunks_of(long long numel, int chunk) { return (numel + chunk - 1) / chunk; }
 
 }  // namespace
 
@@ -188,8 +230,8 @@ using namespace gml;
 extern "C" size_t gml_sqnorm_workspace_bytes(const int64_t* numel_host, int32_t n_tensors) {
   if (!numel_host || n_tensors <= 0) return 0;
   long long chunks = 0;
-  for (int i = 0; i < n_tensors; ++i) chunks += chunks_of(numel_host[i]);
-  return 256 + (size_t)chunks * sizeof(double);  // [counter | pad][partials]
+  for (int i = 0; i < n_tensors; ++i) chunks += chunks_of(numel_host[i], kMinChunk);
+  return 256 + (size_t)chunks * sizeof(double);  // per-chunk partials (sized for the smallest chunk a variant uses)
 }
 
 extern "C" int gml_multi_tensor_sqnorm(const void* const* tensors_host, const int64_t* numel_host,
@@ -200,12 +242,12 @@ extern "C" int gml_multi_tensor_sqnorm(const void* const* tensors_host, const in
     return GML_E_BADARG;
   if (workspace_bytes < gml_sqnorm_workspace_bytes(numel_host, n_tensors)) return GML_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  unsigned int* counter = static_cast<unsigned int*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
-  // The counter must start at zero: the kernel restores it, so zero it only on first use is not
-  // knowable here -> a 4-byte async memset per call (stream ordered, negligible).
-  GML_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
   static thread_local SqnormTable tab;  // 14 KB: keep it off the stack
+  static const int kChunkOf[4] = {4096, 2048, 1024, 8192};
+  const int chunk = kChunkOf[g_sq_variant & 3];
+  const bool pdl = !(g_sq_variant & 4);
+  const int bps = (g_sq_variant >> 3) & 15;  // blocks per SM (0 = 8)
   for (int base = 0; base < n_tensors; base += kMaxTensors) {
     const int cnt = (n_tensors - base) < kMaxTensors ? (n_tensors - base) : kMaxTensors;
     long long chunks = 0;
@@ -218,17 +260,46 @@ extern "C" int gml_multi_tensor_sqnorm(const void* const* tensors_host, const in
       tab.mask[i] = (unsigned char)(bucket_mask_host[base + i] & 15);
       tab.kind[i] = (unsigned char)kind_host[base + i];
       tab.chunk_start[i] = (int)chunks;
-      chunks += chunks_of(ne);
+      chunks += chunks_of(ne, chunk);
       if (chunks > 0x7fffffffLL) return GML_E_UNSUPPORTED;
     }
     tab.chunk_start[cnt] = (int)chunks;
     tab.n_tensors = cnt;
-    int grid = kNumSMs * 8;
-    if (chunks < grid) grid = chunks > 0 ? (int)chunks : 1;
-    LaunchScope ls(kTagSqnorm, st);
-    sqnorm_kernel<<<grid, kSqThreads, 0, st>>>(tab, partial, counter, out8, per_tensor ? per_tensor + base : nullptr,
-                                               base > 0 ? 1 : 0);
-    GML_LAUNCH_CHECK();
+    // every warp the same number of chunks: rounds = ceil(chunks / resident warps), warps = ceil(chunks / rounds)
+    const int wpb = kSqThreads / 32;
+    const long long max_warps = (long long)kNumSMs * (bps ? bps : 8) * wpb;
+    const long long rounds = chunks > 0 ? (chunks + max_warps - 1) / max_warps : 1;
+    const long long warps = chunks > 0 ? (chunks + rounds - 1) / rounds : 1;
+    const int grid = (int)((warps + wpb - 1) / wpb);
+    double* pt = per_tensor ? per_tensor + base : nullptr;
+    const int acc = base > 0 ? 1 : 0;
+    {
+      LaunchScope ls(kTagSqnorm, st);
+      switch (g_sq_variant & 3) {
+        case 0: sqnorm_scan_kernel<4096><<<grid, kSqThreads, 0, st>>>(tab, partial); break;
+        case 1: sqnorm_scan_kernel<2048><<<grid, kSqThreads, 0, st>>>(tab, partial); break;
+        case 2: sqnorm_scan_kernel<1024><<<grid, kSqThreads, 0, st>>>(tab, partial); break;
+        default: sqnorm_scan_kernel<8192><<<grid, kSqThreads, 0, st>>>(tab, partial); break;
+      }
+      GML_LAUNCH_CHECK();
+    }
+    {
+      LaunchScope ls(kTagSqnorm, st);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kFoldCluster);
+      cfg.blockDim = dim3(kFoldThreads);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kFoldCluster;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl ? 2 : 1;
+      GML_CUDA_TRY(cudaLaunchKernelEx(&cfg, sqnorm_fold_kernel, tab, (const double*)partial, out8, pt, acc));
+    }
   }
   return GML_OK;
 }

@@ -199,7 +199,9 @@ int gml_mmtm_bwd(const float* grad_a_out, const float* grad_b_out, const float* 
  * tensors_host[i] / numel_host[i] / bucket_mask_host[i] describe n_tensors fp32 device
  * arrays (parameters and their gradients are simply listed as separate entries with
  * kind_host[i] = 0 for a weight, 1 for a gradient).  Host arrays are consumed before the
- * call returns (they travel as kernel parameters).
+ * call returns (they travel as kernel parameters).  Two launches per 1024 tensors: a scan
+ * (one warp per 4096-element chunk) and a one-cluster fold started with programmatic
+ * dependent launch; no host synchronisation, no memset, graph-capturable.
  * out [8] doubles (device): {wn_main0, wn_main1, wn_bypass0, wn_bypass1,
  *                           gn_main0, gn_main1, gn_bypass0, gn_bypass1}.
  * per_tensor (device, n_tensors doubles) optionally receives each tensor's own sum.

@@ -45,7 +45,7 @@ def _sqnorm_raw(tensors, masks, kinds):
 
 def test_sqnorm_ragged_sizes_and_alignment():
     rs = np.random.RandomState(0)
-    sizes = [1, 3, 4, 5, 255, 4095, 4096, 4097, 8192, 100003, 1 << 20, 0, 7]
+    sizes = [1, 3, 4, 5, 255, 2047, 2048, 2049, 4095, 4096, 4097, 8192, 100003, 1 << 20, 0, 7]
     tensors, masks, kinds = [], [], []
     for i, s in enumerate(sizes):
         buf = torch.from_numpy(rs.standard_normal(s + 3).astype(np.float32)).to(DEV)
