@@ -253,7 +253,7 @@ extern int g_fused_stash_kb;
 extern int g_sq_variant;
 extern int g_tile_kind, g_tile_lag, g_tile_gemm_ctas, g_tile_m, g_tile_chunk_kb, g_tile_min_mb;
 extern long long* g_tile_stats;
-extern int g_tile_nodeps, g_tile_ksplit_tiles;
+extern int g_tile_nodeps, g_tile_ksplit_tiles, g_tile_switch, g_tile_trace_only, g_tile_rpol, g_tile_max_slots, g_tile_split_copies, g_tile_draw, g_tile_chunk_kb_fwd, g_tile_min_mb_light;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -291,6 +291,14 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "tile_ksplit_tiles")) { g_tile_ksplit_tiles = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "tile_nodeps")) { g_tile_nodeps = (int)value; return GML_OK; }
   if (!strcmp(name, "tile_stats_ptr")) { g_tile_stats = reinterpret_cast<long long*>(value); return GML_OK; }
+  if (!strcmp(name, "tile_trace_only")) { g_tile_trace_only = value != 0; return GML_OK; }
+  if (!strcmp(name, "tile_rpol")) { g_tile_rpol = (int)value; return GML_OK; }
+  if (!strcmp(name, "tile_max_slots")) { g_tile_max_slots = (int)value; return GML_OK; }
+  if (!strcmp(name, "tile_split_copies")) { g_tile_split_copies = value < 1 ? 1 : (int)value; return GML_OK; }
+  if (!strcmp(name, "tile_draw")) { g_tile_draw = value < 1 ? 1 : (value > 64 ? 64 : (int)value); return GML_OK; }
+  if (!strcmp(name, "tile_chunk_kb_fwd")) { g_tile_chunk_kb_fwd = value < 1 ? 1 : (value > 100 ? 100 : (int)value); return GML_OK; }
+  if (!strcmp(name, "tile_min_mb_light")) { g_tile_min_mb_light = value < 0 ? 0 : (int)value; return GML_OK; }
+  if (!strcmp(name, "tile_switch")) { g_tile_switch = value != 0; return GML_OK; }
   if (!strcmp(name, "sq_variant")) { g_sq_variant = (int)value & 127; return GML_OK; }
   if (!strcmp(name, "tile_min_mb")) { g_tile_min_mb = value < 0 ? 0 : (int)value; return GML_OK; }
   if (!strcmp(name, "fused_threads")) {
@@ -375,7 +383,7 @@ extern "C" int gml_mmtm_fwd(const float* a, const float* b, float* a_out, float*
                         tile_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode) &&
                         workspace_bytes >= tile_fwd_workspace_bytes(d.n, d.c_v, d.hw_v, d.d);
   if ((flags & GML_F_FORCE_TILE) && !can_tile) return GML_E_UNSUPPORTED;
-  if (can_tile && ((flags & GML_F_FORCE_TILE) || tile_preferred(d.n, d.c_v, d.hw_v, d.d))) {
+  if (can_tile && ((flags & GML_F_FORCE_TILE) || tile_preferred(d.n, d.c_v, d.hw_v, d.d, false))) {
     FusedFwdArgs fa{a, b, a_out, b_out, w_sq, b_sq, w_v, b_v, w_s, b_s, z, h, g_a, g_b, run_v, run_s,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
     const int rc = launch_tile_fwd(fa, gate_sum, update ? run_v : nullptr, update ? run_s : nullptr, (float)step,
@@ -516,7 +524,7 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
                         tile_supported(d.n, d.c_v, d.c_s, d.hw_v, d.hw_s, d.d, mode);
   if ((flags & GML_F_FORCE_TILE) && !can_tile) return GML_E_UNSUPPORTED;
   bool tiled = false, fused_done = false;
-  if (can_tile && ((flags & GML_F_FORCE_TILE) || tile_preferred(d.n, d.c_v, d.hw_v, d.d))) {
+  if (can_tile && ((flags & GML_F_FORCE_TILE) || tile_preferred(d.n, d.c_v, d.hw_v, d.d, true))) {
     FusedBwdArgs fb{go_a, go_b, a, b, w_sq, w_v, w_s, z, h, g_a, g_b, run_v, run_s, d_a, d_b, de_a, de_b, dh,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
     const int rc = launch_tile_bwd(fb, dz, d_b_v, d_b_s, d_b_sq, tile_ws, tile_bytes, st);

@@ -91,6 +91,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t policy) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
@@ -118,5 +123,8 @@ __device__ __forceinline__ void stg_hint(float4* p, const float4& v, uint64_t po
 }
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU.EX2 + MUFU.RCP: ~2 ulp of exp and 1 ulp of the reciprocal, i.e. a few 1e-7 relative on the gate (the parity
+// tolerance is 1e-5); used where the sigmoid sits on a latency chain (GEMM epilogue of the tile pipeline)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 }  // namespace gml

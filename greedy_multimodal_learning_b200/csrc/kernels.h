@@ -120,7 +120,7 @@ int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st);
 
 // ---- tile pipeline (tile_kernels.cu): one persistent kernel per block and direction, normal mode -----------------
 bool tile_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mode);
-bool tile_preferred(int n, int c, int hw, int d);
+bool tile_preferred(int n, int c, int hw, int d, bool bwd);
 size_t tile_fwd_workspace_bytes(int n, int c, int hw, int d);
 size_t tile_bwd_workspace_bytes(int n, int c, int hw, int d);
 // gate_sum / run_v / run_s may be nullptr (no column sum / no running-mean update inside the kernel)

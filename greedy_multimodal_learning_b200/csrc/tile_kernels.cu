@@ -43,10 +43,20 @@ int g_tile_kind = 0;        // tunable "tile_kind": 0 automatic, 1 whenever the 
 int g_tile_lag = 0;         // tunable "tile_lag": tiles between a tile's R and S stage in the stream queue (0 = automatic)
 int g_tile_gemm_ctas = 0;   // tunable "tile_gemm_ctas": 0 = from the FLOP/byte estimate
 int g_tile_m = 0;           // tunable "tile_m": samples per tile, 0 = automatic (~25 MB of feature map per tile)
-int g_tile_chunk_kb = 28;   // tunable "tile_chunk_kb": upper bound of a chunk (one work item) in KB
-int g_tile_min_mb = 96;     // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality
+int g_tile_chunk_kb = 28;   // tunable "tile_chunk_kb": upper bound of a backward chunk (one work item) in KB; a slot holds two
+int g_tile_chunk_kb_fwd = 56;  // tunable "tile_chunk_kb_fwd": the same for the forward (one buffer per slot).  The loader warp
+                            // spends ~1000 cycles per item whatever its size, so fewer, larger items stream faster:
+                            // forward 128x28^2 0.434 -> 0.379 ms, 256x14^2 0.236 -> 0.213 ms (profiles/r2_sweep.md)
+int g_tile_min_mb_light = 190;  // tunable "tile_min_mb_light": the same threshold for the forward of blocks with < 1 MB of weights
+int g_tile_min_mb = 96;     // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality (forward: half of it)
 int g_tile_ksplit_tiles = 0;  // tunable "tile_ksplit_tiles": k-tiles per split-K item (0 = no split-K: the deep pipeline hides the
                             // chain latency, and partial planes + folds cost more GEMM-CTA time than they save)
+int g_tile_switch = 1;      // tunable "tile_switch": GEMM CTAs join the stream role once the GEMM tickets are exhausted
+int g_tile_trace_only = 0;  // tunable "tile_trace_only" (with tile_stats_ptr): timeline rows only
+int g_tile_rpol = 0;        // tunable "tile_rpol": L2 policy of the R-stage reads (0 evict_last, 1 evict_first, 2 evict_normal)
+int g_tile_max_slots = 0;   // tunable "tile_max_slots": cap on the slot ring (0 = as many as fit)
+int g_tile_split_copies = 1;
+int g_tile_draw = 4;        // tunable "tile_draw": stream tickets per draw (two draws are kept in flight)
 int g_tile_nodeps = 0;      // debug/measurement ONLY (wrong results): S items do not wait for the gates
 long long* g_tile_stats = nullptr;  // debug: per-CTA cycle breakdown (device buffer, 16 slots per CTA)
 
@@ -111,6 +121,11 @@ struct TileParams {
   unsigned* ctr;
   float* part;
   size_t part_tile_floats;   // partial planes of one tile: (sum over stages of n_tiles * splits) * 128 * 128
+  int gemm_joins_stream;
+  int draw;                  // stream tickets per draw
+  int split_copies;          // measurement: forward R chunks are fetched as this many bulk copies
+  int rpol;                  // L2 policy of the R-stage reads: 0 evict_last, 1 evict_first, 2 evict_normal
+  int trace_only;            // with `stats`: only the cheap timeline rows, no per-CTA cycle accounting
   int nodeps;                // measurement only: S items skip their dependency wait (results are garbage)
   long long* stats;          // debug (tunable "tile_stats_ptr"): 16 clock64 sums per CTA, or nullptr
 };
@@ -136,6 +151,15 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 // bounded wait on a monotonically increasing counter written with release semantics by other CTAs
+// timeline trace (tunable tile_stats_ptr, measurement only): absolute globaltimer ns
+constexpr int kTraceGemmRow = 400, kTraceTileRow = 700, kTraceStartRow = 399;
+__device__ __forceinline__ void trace_min(long long* stats, int row, int col) {
+  if (stats) atomicMin(reinterpret_cast<unsigned long long*>(stats) + (size_t)row * 16 + col, global_ns());
+}
+__device__ __forceinline__ void trace_max(long long* stats, int row, int col) {
+  if (stats) atomicMax(reinterpret_cast<unsigned long long*>(stats) + (size_t)row * 16 + col, global_ns());
+}
+
 __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned need) {
   if (ld_acquire_u32(p) >= need) return;
   const unsigned long long t0 = global_ns();
@@ -224,7 +248,8 @@ __device__ __forceinline__ void mbar_expect_tx_el(uint32_t bar, uint32_t bytes) 
 // with ONE release per (CTA, tile) instead of a gpu-scope fence per warp and item.
 __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMeta* metas, uint64_t* full, uint64_t* empty,
                               long long* st_cycles, int lane) {
-  const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
+  const uint64_t pol_drop = policy_evict_first();
+  const uint64_t pol_keep = P.rpol == 0 ? policy_evict_last() : (P.rpol == 1 ? pol_drop : policy_evict_normal());
   const int T = P.n_tiles, nseg = 2 * (T + P.lag);
   const uint32_t smem0 = u_smem_addr(sm.base), full0 = u_smem_addr(full);
   const uint32_t vec_bytes = (uint32_t)P.p * 4u;
@@ -239,6 +264,8 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
     seg_kind = (seg & 1) ? kItemS : kItemR;
     seg_t = (seg & 1) ? (seg >> 1) - P.lag : (seg >> 1);
     if (seg_t < 0 || seg_t >= T) { seg_chunks = 0; return; }
+    // measurement only: 5 = R stage alone, 6 = S stage alone (no GEMM work, no dependencies; results are garbage)
+    if (((P.nodeps == 5 || P.nodeps == 7) && seg_kind == kItemS) || ((P.nodeps == 6 || P.nodeps == 8) && seg_kind == kItemR)) { seg_chunks = 0; return; }
     seg_chunks = (unsigned)(tile_rows(P, seg_t) * P.cps);
     seg_end = seg_start + 2u * seg_chunks;
     seg_n0 = seg_t * P.m_tile;
@@ -255,8 +282,9 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
   // published yet); `rec` packs one byte per slot: 0x80 | (tile & 0x7f) for an R item, 0 for an S item.
   unsigned long long iss = 0, fin = 0, rec = 0;
   int flush_tile = 0;
-  long long c_empty = 0, c_dep = 0;
+  long long c_empty = 0, c_dep = 0, c_head = 0, c_issue = 0, c_draw = 0, t_prev = 0;
   const bool timing = st_cycles != nullptr;
+  if (timing) t_prev = clk();
 
   auto account = [&](int s_) {   // the item in slot s_ is finished
     const unsigned r = (unsigned)(rec >> (8 * s_)) & 0xffu;
@@ -288,20 +316,18 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
     while (flush_tile < T && (exhausted || seg > 2 * flush_tile) && (fin & 0xffffull) == (iss & 0xffffull)) {
       const unsigned cnt = (unsigned)(iss & 0xffffull);
       if (cnt && lane == 0) red_release_add(tile_ctr(P, flush_tile) + 0, cnt);
+      if (cnt && lane == 0 && flush_tile < 64) trace_max(P.stats, kTraceTileRow + flush_tile, 1);
       iss >>= 16; fin >>= 16;
       ++flush_tile;
     }
     __syncwarp();
   };
 
-  // tickets are drawn kDraw at a time and one draw ahead: lane 0 keeps the pending result in a register and the warp
-  // only reads it (shuffle) when the current batch is used up, so the atomic's round trip overlaps those items
-  constexpr unsigned kDraw = 4;
-  unsigned pending = 0;
-  if (lane == 0) pending = atomicAdd(&P.ctr[0], kDraw);
-  unsigned cur = __shfl_sync(0xffffffffu, pending, 0);
-  for (;;) {
-    if (lane == 0) pending = atomicAdd(&P.ctr[0], kDraw);
+  // Tickets are drawn kDraw at a time and TWO draws ahead.  The atomic's round trip is 2-4 us while the memory system
+  // is saturated; with four tickets drawn one batch ahead the loader spent ~0.9 us per item waiting for its next
+  // batch, which capped a CTA at one 28 KB chunk per 0.9 us whatever the chunk size (profiles/r2_tile_loader.md).
+  const unsigned kDraw = (unsigned)P.draw;
+  auto run_batch = [&](unsigned cur) -> bool {   // true when the queue is exhausted
     for (unsigned ticket = cur; ticket < cur + kDraw; ++ticket) {
       while (ticket >= seg_end) next_segment();
       if (seg >= nseg) {  // queue exhausted: finish the bookkeeping, then tell the workers
@@ -312,10 +338,13 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
             metas[s_].kind = kItemStop;
             u_mbar_arrive(&full[s_]);
           }
-          if (timing) { st_cycles[2] = c_empty; st_cycles[3] = c_dep; st_cycles[1] = uses; }
+          if (timing) {
+            st_cycles[2] = c_empty; st_cycles[3] = c_dep; st_cycles[1] = uses;
+            st_cycles[8] = c_head; st_cycles[9] = c_issue; st_cycles[10] = c_draw;
+          }
         }
         __syncwarp();
-        return;
+        return true;
       }
       const long long t0 = timing ? clk() : 0;
       if (uses >= (unsigned)P.slots) retire(uses - (unsigned)P.slots + 1u);  // frees this item's slot
@@ -344,10 +373,12 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
           }
         }
         ready_tile = seg_t;
+        if (lane == 0 && seg_t < 64) trace_max(P.stats, kTraceTileRow + seg_t, 2);
         asm volatile("fence.proxy.async;" ::: "memory");  // the gates were written through the generic proxy
       }
       const long long t2 = timing ? clk() : 0;
       c_empty += t1 - t0; c_dep += t2 - t1;
+      if (timing) c_head += t0 - t_prev;
       if (lane == 0) {
         // first plane of the chunk = sample n, channel c0 (a chunk never straddles samples: P divides C)
         const int nl = P.cps == 1 ? (int)ch : (int)__umulhi(ch, P.cps_magic);  // ch / cps
@@ -373,7 +404,13 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
           bulk_g2s_elect(sgate, P.gate[mod] + q0, vec_bytes, bar, pol_keep);
         } else {
           mbar_expect_tx_el(bar, P.chunk_bytes);
-          bulk_g2s_elect(sbase, P.x[mod] + off, P.chunk_bytes, bar, pol_keep);
+          if (P.split_copies > 1) {  // measurement: the same bytes as several smaller bulk copies
+            const uint32_t part = P.chunk_bytes / (uint32_t)P.split_copies;
+            for (int j = 0; j < P.split_copies; ++j)
+              bulk_g2s_elect(sbase + j * part, reinterpret_cast<const char*>(P.x[mod] + off) + (size_t)j * part, part, bar, pol_keep);
+          } else {
+            bulk_g2s_elect(sbase, P.x[mod] + off, P.chunk_bytes, bar, pol_keep);
+          }
         }
       } else {
         mbar_expect_tx_el(bar, P.chunk_bytes + vec_bytes * (P.bwd ? 2u : 1u));
@@ -381,10 +418,32 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
         bulk_g2s_elect(sgate, P.gate[mod] + q0, vec_bytes, bar, pol_drop);
         if (P.bwd) bulk_g2s_elect(sgate + vec_bytes, P.add[mod] + q0, vec_bytes, bar, pol_drop);
       }
+      if (lane == 0 && P.stats && seg_t < 64 && idx == 0) {  // first chunk of a segment only: keeps the trace cheap
+        if (seg_kind == kItemR) trace_min(P.stats, kTraceTileRow + seg_t, 0);
+        else trace_min(P.stats, kTraceTileRow + seg_t, 3);
+      }
+      if (lane == 0 && P.stats && seg_t < 64 && seg_kind == kItemS && ticket + 1 == seg_end)
+        trace_max(P.stats, kTraceTileRow + seg_t, 4);
       ++uses;
       if (++slot == P.slots) slot = 0;
+      if (timing) { t_prev = clk(); c_issue += t_prev - t2; }
     }
-    cur = __shfl_sync(0xffffffffu, pending, 0);
+    return false;
+  };
+  unsigned pend_a = 0, pend_b = 0;
+  if (lane == 0) {
+    pend_a = atomicAdd(&P.ctr[0], kDraw);
+    pend_b = atomicAdd(&P.ctr[0], kDraw);
+  }
+  unsigned cur = __shfl_sync(0xffffffffu, pend_a, 0);
+  for (;;) {
+    // (two named registers alternate so that no instruction touches a draw before the batch it is needed for)
+    if (lane == 0) pend_a = atomicAdd(&P.ctr[0], kDraw);
+    if (run_batch(cur)) return;
+    { const long long d0 = timing ? clk() : 0; cur = __shfl_sync(0xffffffffu, pend_b, 0); if (timing) { const long long d1 = clk(); c_draw += d1 - d0; t_prev = d1; } }
+    if (lane == 0) pend_b = atomicAdd(&P.ctr[0], kDraw);
+    if (run_batch(cur)) return;
+    { const long long d0 = timing ? clk() : 0; cur = __shfl_sync(0xffffffffu, pend_a, 0); if (timing) { const long long d1 = clk(); c_draw += d1 - d0; t_prev = d1; } }
   }
 }
 
@@ -542,7 +601,7 @@ __device__ void stream_workers(const TileParams& P, const StreamSmem& sm, const 
     const long long t1 = timing ? clk() : 0;
     const SlotMeta m = metas[slot];
     if (m.kind == kItemStop) break;
-    if (P.nodeps == 2 || P.nodeps == 3) {  // measurement only: no compute, just recycle the slot
+    if (P.nodeps == 2 || P.nodeps == 3 || P.nodeps >= 7) {  // measurement only (7 / 8: R / S stage alone, loads only): no compute, just recycle the slot
       if (P.nodeps == 3 && lane == 0) { volatile float sink = sm.chunk(slot, 0)[tid]; (void)sink; }
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(&empty[slot]);
@@ -752,7 +811,7 @@ __device__ __noinline__ void gemm_store_rows(const TileParams& P, const GemmStag
     if (epi == kEpiRelu) {
       v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
     } else if (epi == kEpiSigmoid) {
-      v.x = sigmoidf_ref(v.x); v.y = sigmoidf_ref(v.y); v.z = sigmoidf_ref(v.z); v.w = sigmoidf_ref(v.w);
+      v.x = sigmoidf_fast(v.x); v.y = sigmoidf_fast(v.y); v.z = sigmoidf_fast(v.z); v.w = sigmoidf_fast(v.w);
     } else if (epi == kEpiMask) {
       const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + (size_t)(m0 + r) * g.ldmask + col));
       v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
@@ -873,7 +932,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     if (tid == 0) s_ticket = atomicAdd(&P.ctr[1], 1u);
     __syncthreads();
     const unsigned ticket = s_ticket;
-    if (ticket >= total) break;
+    if (ticket >= total || P.nodeps >= 5) break;
     if (ticket >= per_tile * (unsigned)T) {
       // ---- column-sum item: needs every tile's R, F1 and F2 -----------------------------------------------------
       if (tid == 0) {
@@ -900,13 +959,16 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     it.split = rr - it.ntile * g.splits;
     unsigned* tc = tile_ctr(P, it.tile);
     const long long tg0 = timing ? clk() : 0;
+    const unsigned long long t_item0 = (tid == 0 && P.stats) ? global_ns() : 0ull;
     if (tid == 0) {
       if (P.w_cat_t) wait_counter(&P.ctr[3], (unsigned)P.n_gemm);
       if (it.stage == 0) {
         const unsigned rneed = 2u * (unsigned)((size_t)tile_rows(P, it.tile) * P.c / P.p);  // one per R item
         wait_counter(tc + 0, rneed);
         // the partial planes of this ring position were last used by tile - kRingTiles: fully folded?
-        if (it.tile >= kRingTiles) wait_counter(tile_ctr(P, it.tile - kRingTiles) + 2, (unsigned)P.st[1].n_tiles);
+        // (only with split-K: without it this would hold every tile's chain behind the one four tiles ahead --
+        // measured as a 25 us stall per tile at 512x7^2, profiles/r2_tile_timeline_512.txt)
+        if (it.tile >= kRingTiles && (P.st[0].splits > 1 || P.st[1].splits > 1)) wait_counter(tile_ctr(P, it.tile - kRingTiles) + 2, (unsigned)P.st[1].n_tiles);
       } else {
         wait_counter(tc + 1, (unsigned)P.st[0].n_tiles);
       }
@@ -916,9 +978,14 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     const int k_end = min(g.k_total, k_begin + g.k_per_split);
     const int nk = k_end > k_begin ? (k_end - k_begin + UK - 1) / UK : 0;
     const long long tg1 = timing ? clk() : 0;
+    if (tid == 0 && P.stats && ticket < 256) {
+      long long* row = P.stats + (size_t)(kTraceGemmRow + ticket) * 16;
+      row[0] = it.tile; row[1] = it.stage; row[2] = it.ntile; row[3] = grank; row[4] = (long long)t_item0; row[5] = (long long)global_ns();
+    }
     gemm_item_mainloop(P, g, it, u_smem, bars, tmem, kbase, gbase, nk, sum, warp, lane, tid,
                        st_cycles ? P.stats + (size_t)(gridDim.x + blockIdx.x) * 16 : nullptr);
     const long long tg2 = timing ? clk() : 0;
+    if (tid == 0 && P.stats && ticket < 256) P.stats[(size_t)(kTraceGemmRow + ticket) * 16 + 6] = (long long)global_ns();
     kbase += (uint32_t)nk;
     gbase += (uint32_t)((nk + UGROUP - 1) / UGROUP);
 
@@ -974,6 +1041,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
         else { st_cycles[14] += tg5 - tg4; st_cycles[15] += t6 - tg5; }
       }
       if (tid == 0) red_release_add(tc + 1 + it.stage, 1u);
+      if (tid == 0 && P.stats && ticket < 256) P.stats[(size_t)(kTraceGemmRow + ticket) * 16 + 7] = (long long)global_ns();
     }
     if (timing) {
       const long long tg6 = clk();
@@ -1003,12 +1071,19 @@ __global__ void __launch_bounds__(kThreads, 1) tile_pipeline_kernel(const __grid
   if (tid == 0) s_role = atomicAdd(&P.ctr[2], 1u);
   __syncthreads();
   const int role = (int)s_role;
-  long long* st_cycles = P.stats ? P.stats + (size_t)blockIdx.x * 16 : nullptr;
+  long long* st_cycles = (P.stats && !P.trace_only) ? P.stats + (size_t)blockIdx.x * 16 : nullptr;
   const long long t_begin = st_cycles ? clk() : 0;
+  if (tid == 0) trace_min(P.stats, kTraceStartRow, 0);
   if (role < P.n_gemm) {
     gemm_role(P, role, smem, tid, st_cycles);
     if (st_cycles && tid == 0) { st_cycles[0] = 1; st_cycles[7] = clk() - t_begin; }
-    return;
+    // The last GEMM ticket is drawn when the last tile's reduce stage is complete, i.e. when the second half of the
+    // stream queue (S items of the last `lag` tiles) is still ahead.  The CTA then joins the stream role: tickets are
+    // drawn dynamically, so a late joiner simply takes the next ones.  (512x7^2: 48 of 148 SMs would otherwise idle
+    // for the last ~60 % of the launch.)
+    if (!P.gemm_joins_stream) return;
+    st_cycles = nullptr;
+    __syncthreads();
   }
   if (tid == 0) {
     for (int s = 0; s < P.slots; ++s) { u_mbar_init(&s_full[s], 1); u_mbar_init(&s_empty[s], P.wps); }
@@ -1052,7 +1127,10 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   if ((long long)n * c >= (1LL << 31) / 2) return false;
   TileCfg f;
   // chunk: P planes, P | C, P % 4 == 0 (16-byte aligned gate vectors and chunk bytes), as large as the bound allows
-  const size_t bound = (size_t)g_tile_chunk_kb * 1024;
+  // forward chunks are doubled once a modality has >= ~190 MB: with fewer items in total the finer interleave of R and
+  // S items matters more than the per-item cost (256x14^2 at batch 512: 0.129 ms with 28 KB vs 0.137 ms with 56 KB)
+  const bool big_fwd = !bwd && (size_t)n * c * hw * 4 >= ((size_t)g_tile_min_mb_light << 20);
+  const size_t bound = (size_t)(big_fwd ? g_tile_chunk_kb_fwd : g_tile_chunk_kb) * 1024;
   f.p = 0;
   for (int p = c; p >= 4; --p) {
     if (c % p || p % 4) continue;
@@ -1080,6 +1158,7 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   int slots = (int)(budget / f.slot_bytes);
   if (slots < 2) return false;
   slots = slots >= 8 ? 8 : (slots >= 4 ? 4 : 2);  // a power of two; a group of warps owns two slots
+  if (g_tile_max_slots >= 2 && slots > g_tile_max_slots) slots = g_tile_max_slots >= 8 ? 8 : (g_tile_max_slots >= 4 ? 4 : 2);
   f.slots = slots;
   f.wps = (U_PRODUCERS / 32) / (slots / 2);
   size_t sm = (size_t)slots * f.slot_bytes;
@@ -1183,6 +1262,11 @@ void fill_common(TileParams& P, const TileCfg& f, int n, int c, int hw, int d, b
   P.n_cs = 0;
   P.stats = g_tile_stats;
   P.nodeps = g_tile_nodeps;
+  P.gemm_joins_stream = g_tile_switch;
+  P.draw = g_tile_draw;
+  P.split_copies = g_tile_split_copies;
+  P.rpol = g_tile_rpol;
+  P.trace_only = g_tile_trace_only;
   P.w_cat_t = nullptr; P.w_sq_t = nullptr; P.w_v = P.w_s = P.w_sq = nullptr;
 }
 
@@ -1225,11 +1309,14 @@ bool tile_supported(int n, int c_v, int c_s, int hw_v, int hw_s, int d, int mode
 // stage re-reads from HBM (the FC chain of a tile takes longer than L2 can hold the tile), i.e. it moves 6u / 8u.  That
 // beats the streaming multi-kernel path and the cluster kernels' per-group weight re-reads for the weight-heavy blocks
 // (C >= 256) once the batch is large; the 128-channel block stays on the cluster kernels (4u / 6u from L2-resident groups).
-bool tile_preferred(int n, int c, int hw, int d) {
+bool tile_preferred(int n, int c, int hw, int d, bool bwd) {
   if (g_tile_kind == 1) return true;
   const size_t u = (size_t)n * c * hw * 4;
   const size_t w_bytes = (size_t)16 * c * d;
-  return w_bytes >= (1u << 20) && u >= ((size_t)g_tile_min_mb << 20);
+  if (w_bytes >= (1u << 20)) return u >= ((size_t)g_tile_min_mb << 20) / (bwd ? 1 : 2);
+  // light-weight blocks (128 channels): the cluster kernels move 4u / 6u and win the backward; the forward of a large
+  // batch is faster through the pipeline's 56 KB items
+  return !bwd && u >= ((size_t)g_tile_min_mb_light << 20);
 }
 
 size_t tile_fwd_workspace_bytes(int n, int c, int hw, int d) {

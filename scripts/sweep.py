@@ -22,6 +22,68 @@ VARIANTS = {
     # name: (flags, tunables)
     "auto": (0, {}),
     "old": (0, {"tile_kind": 2}),
+    "noswitch": (0, {"tile_switch": 0}),
+    "x_nodeps1": (L.F_FORCE_TILE, {"tile_nodeps": 1}),
+    "x_nodeps2": (L.F_FORCE_TILE, {"tile_nodeps": 2}),
+    "x_nodeps3": (L.F_FORCE_TILE, {"tile_nodeps": 3}),
+    "x_nodeps4": (L.F_FORCE_TILE, {"tile_nodeps": 4}),
+    "x_nodeps1_g3": (L.F_FORCE_TILE, {"tile_nodeps": 1, "tile_gemm_ctas": 3}),
+    "x_nodeps2_g3": (L.F_FORCE_TILE, {"tile_nodeps": 2, "tile_gemm_ctas": 3}),
+    "x_nodeps4_g3": (L.F_FORCE_TILE, {"tile_nodeps": 4, "tile_gemm_ctas": 3}),
+    "k_ks8_g72": (L.F_FORCE_TILE, {"tile_ksplit_tiles": 8, "tile_gemm_ctas": 72}),
+    "k_ks8_g48": (L.F_FORCE_TILE, {"tile_ksplit_tiles": 8, "tile_gemm_ctas": 48}),
+    "k_ks16_g72": (L.F_FORCE_TILE, {"tile_ksplit_tiles": 16, "tile_gemm_ctas": 72}),
+    "k_ks4_g72": (L.F_FORCE_TILE, {"tile_ksplit_tiles": 4, "tile_gemm_ctas": 72}),
+    "k_ks8_g72_l3": (L.F_FORCE_TILE, {"tile_ksplit_tiles": 8, "tile_gemm_ctas": 72, "tile_lag": 3}),
+    "k_ks8_g72_l4": (L.F_FORCE_TILE, {"tile_ksplit_tiles": 8, "tile_gemm_ctas": 72, "tile_lag": 4}),
+    "k_g72_l4": (L.F_FORCE_TILE, {"tile_gemm_ctas": 72, "tile_lag": 4}),
+    "k_g72_l3": (L.F_FORCE_TILE, {"tile_gemm_ctas": 72, "tile_lag": 3}),
+    "k_g72_m64": (L.F_FORCE_TILE, {"tile_gemm_ctas": 72, "tile_m": 64}),
+    "k_ks8_g72_m64": (L.F_FORCE_TILE, {"tile_ksplit_tiles": 8, "tile_gemm_ctas": 72, "tile_m": 64}),
+    "x_ronly": (L.F_FORCE_TILE, {"tile_nodeps": 5}),
+    "x_sonly": (L.F_FORCE_TILE, {"tile_nodeps": 6}),
+    "x_ronly_c14": (L.F_FORCE_TILE, {"tile_nodeps": 5, "tile_chunk_kb": 14}),
+    "x_sonly_c14": (L.F_FORCE_TILE, {"tile_nodeps": 6, "tile_chunk_kb": 14}),
+    "x_ronly_c56": (L.F_FORCE_TILE, {"tile_nodeps": 5, "tile_chunk_kb": 56}),
+    "p_ronly_p1": (L.F_FORCE_TILE, {"tile_nodeps": 5, "tile_rpol": 1}),
+    "p_ronly_p2": (L.F_FORCE_TILE, {"tile_nodeps": 5, "tile_rpol": 2}),
+    "p_tile_p1": (L.F_FORCE_TILE, {"tile_rpol": 1}),
+    "p_tile_p2": (L.F_FORCE_TILE, {"tile_rpol": 2}),
+    "q_rload": (L.F_FORCE_TILE, {"tile_nodeps": 7}),
+    "q_sload": (L.F_FORCE_TILE, {"tile_nodeps": 8}),
+    "q_rload_c56": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_chunk_kb": 56}),
+    "q_rload_c14": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_chunk_kb": 14}),
+    "s_slots4": (L.F_FORCE_TILE, {"tile_max_slots": 4}),
+    "s_slots2": (L.F_FORCE_TILE, {"tile_max_slots": 2}),
+    "s_slots4_c14": (L.F_FORCE_TILE, {"tile_max_slots": 4, "tile_chunk_kb": 14}),
+    "s_slots8_c14": (L.F_FORCE_TILE, {"tile_max_slots": 8, "tile_chunk_kb": 14}),
+    "s_rload_slots4": (L.F_FORCE_TILE, {"tile_max_slots": 4, "tile_nodeps": 7}),
+    "s_rload_slots2": (L.F_FORCE_TILE, {"tile_max_slots": 2, "tile_nodeps": 7}),
+    "c_rload_x2": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_split_copies": 2}),
+    "c_rload_x4": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_split_copies": 4}),
+    "c_rload_x7": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_split_copies": 7}),
+    "c_rload_c56_x2": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_split_copies": 2, "tile_chunk_kb": 56}),
+    "c_rload_c112": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_chunk_kb": 100}),
+    "d_draw1": (L.F_FORCE_TILE, {"tile_draw": 1}),
+    "d_draw2": (L.F_FORCE_TILE, {"tile_draw": 2}),
+    "d_draw4": (L.F_FORCE_TILE, {"tile_draw": 4}),
+    "d_draw8": (L.F_FORCE_TILE, {"tile_draw": 8}),
+    "d_draw16": (L.F_FORCE_TILE, {"tile_draw": 16}),
+    "d_c56": (L.F_FORCE_TILE, {"tile_chunk_kb": 56}),
+    "d_c40": (L.F_FORCE_TILE, {"tile_chunk_kb": 40}),
+    "f_c28": (L.F_FORCE_TILE, {"tile_chunk_kb_fwd": 28}),
+    "f_c56": (L.F_FORCE_TILE, {"tile_chunk_kb_fwd": 56}),
+    "f_c100": (L.F_FORCE_TILE, {"tile_chunk_kb_fwd": 100}),
+    "x_c14": (L.F_FORCE_TILE, {"tile_chunk_kb": 14}),
+    "x_c56": (L.F_FORCE_TILE, {"tile_chunk_kb": 56}),
+    "sw_g24": (L.F_FORCE_TILE, {"tile_gemm_ctas": 24}),
+    "sw_g56": (L.F_FORCE_TILE, {"tile_gemm_ctas": 56}),
+    "sw_g72": (L.F_FORCE_TILE, {"tile_gemm_ctas": 72}),
+    "sw_l3_g72": (L.F_FORCE_TILE, {"tile_gemm_ctas": 72, "tile_lag": 3}),
+    "sw_l4_g56": (L.F_FORCE_TILE, {"tile_gemm_ctas": 56, "tile_lag": 4}),
+    "sw_l4_g24": (L.F_FORCE_TILE, {"tile_gemm_ctas": 24, "tile_lag": 4}),
+    "sw_l3_g40": (L.F_FORCE_TILE, {"tile_gemm_ctas": 40, "tile_lag": 3}),
+    "sw_tile": (L.F_FORCE_TILE, {}),
     "tile": (L.F_FORCE_TILE, {}),
     "tile_lag1": (L.F_FORCE_TILE, {"tile_lag": 1}),
     "tile_lag3": (L.F_FORCE_TILE, {"tile_lag": 3}),
@@ -172,7 +234,9 @@ def main():
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--variants", default=",".join(VARIANTS))
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
+    ap.add_argument("--shapes", default="", help="comma-separated channel counts to keep (default: all three blocks)")
     args = ap.parse_args()
+    keep = [int(x) for x in args.shapes.split(",") if x]
     lib = L.load()
     dev = torch.device("cuda:0")
     peak, _ = measured_peak()
@@ -180,6 +244,8 @@ def main():
     stream = torch.cuda.current_stream()
     rows = []
     for c, h in SHAPES:
+        if keep and c not in keep:
+            continue
         for n in [int(x) for x in args.batches.split(",")]:
             b = BlockBuffers(torch, L, n, c, h, dev, seed=c)
             u = n * c * h * h * 4
@@ -200,7 +266,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, "tile_switch": 1, "tile_rpol": 0, "tile_max_slots": 0, "tile_split_copies": 1, "tile_draw": 4, "tile_chunk_kb_fwd": 56, "tile_min_mb_light": 190, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 # workspace sizes depend on the tile tunables: re-query for this variant
                 b.ws_bytes = lib.gml_mmtm_bwd_workspace_bytes(b.dims)

@@ -18,6 +18,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--tunables", default="")
+    ap.add_argument("--timeline", action="store_true")
+    ap.add_argument("--shapes", default="")
     args = ap.parse_args()
     lib = L.load()
     dev = torch.device("cuda:0")
@@ -27,6 +29,8 @@ def main():
     stats = torch.zeros(1024 * 16, dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     for c, h in SHAPES:
+        if args.shapes and str(c) not in args.shapes.split(","):
+            continue
         b = BlockBuffers(torch, L, args.n, c, h, dev, seed=c)
         P = lambda t: t.data_ptr()
         w, dw = b.w, b.dw
@@ -46,6 +50,11 @@ def main():
             fn(); fn()
             torch.cuda.synchronize()
             stats.zero_()
+            big = torch.iinfo(torch.int64).max
+            stats.view(-1, 16)[399, 0] = big
+            stats.view(-1, 16)[700:764, 0] = big
+            stats.view(-1, 16)[700:764, 3] = big
+            L.check(lib.gml_set_tunable(b"tile_trace_only", 1 if args.timeline else 0))
             L.check(lib.gml_set_tunable(b"tile_stats_ptr", stats.data_ptr()))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
@@ -65,6 +74,9 @@ def main():
                       "warp0 data-wait %6.0f reduce %6.0f scale %6.0f" % (
                           len(r), r[:, 7].mean() / 1e3, r[:, 1].mean(), r[:, 2].mean() / 1e3, r[:, 3].mean() / 1e3,
                           r[:, 4].mean() / 1e3, r[:, 5].mean() / 1e3, r[:, 6].mean() / 1e3))
+            if len(r):
+                print("        loader per item (cyc): slot-wait %5.0f dep-wait %5.0f head(segment/loop) %5.0f issue(meta+TMA) %5.0f ticket-draw wait %5.0f" % tuple(
+                    float(r[:, i].sum() / r[:, 1].sum()) for i in (2, 3, 8, 9, 10)))
             if len(g):
                 print("  GEMM   CTAs %3d: total %7.0f kcyc | items %5.1f | dep-wait %6.0f main %6.0f epilogue %6.0f "
                       "(kcyc per item: main %.1f epi %.1f)" % (
@@ -78,6 +90,22 @@ def main():
                           "worker0: wait-raw %6.0f split %6.0f drain %6.0f kcyc" % tuple(dbg[:, i].mean() / 1e3 for i in (0, 1, 2, 4, 5, 6)))
                 print("        warp4 store %6.0f fence %6.0f | warp8 fence %6.0f sync %6.0f kcyc" % tuple(
                     (g[:, 12 + i].mean() / 1e3) for i in range(4)))
+            if args.timeline:
+                t0 = float(s_all[399, 0])
+                us = lambda v: (float(v) - t0) / 1e3
+                print("        tile timeline (us from kernel start): R first issue | R last publish | S gates seen (last CTA) | S first issue | S last issue")
+                for t in range(64):
+                    row = s_all[700 + t]
+                    if row[1] == 0:
+                        continue
+                    print("          tile %2d: %7.1f %7.1f %7.1f %7.1f %7.1f" % (t, us(row[0]), us(row[1]), us(row[2]), us(row[3]), us(row[4])))
+                print("        GEMM items: ticket tile stage ntile cta | drawn  deps-ok  main-done  signalled (us)")
+                for k in range(256):
+                    row = s_all[400 + k]
+                    if row[5] == 0:
+                        continue
+                    print("          %3d  t%-2d s%d n%-2d cta%-3d | %7.1f %7.1f %7.1f %7.1f" % (
+                        k, row[0], row[1], row[2], row[3], us(row[4]), us(row[5]), us(row[6]), us(row[7])))
         del b
         torch.cuda.empty_cache()
 
