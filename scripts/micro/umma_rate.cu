@@ -117,7 +117,7 @@ int main() {
   cudaFuncSetAttribute(rate_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(rate_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 2048;
-  for (int mode = 2; mode < 4; ++mode) {
+  for (int mode = 0; mode < 4; ++mode) {
     const int grid = 148;
     for (int kind = 0; kind < 2; ++kind) {
       for (int n : {64, 128, 256}) {
