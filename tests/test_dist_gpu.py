@@ -177,3 +177,45 @@ def test_train_command_line_one_process_per_gpu():
     assert idx0 == idx1 and len(idx0[0]) == 32 and len(set(idx0[0])) == 32
     assert {"history.csv", "history.pickle", "model_best_val.pt", "model_last_epoch.pt"} <= set(files0)
     assert w0 == w1
+
+
+REC_N, REC_C, REC_H = 10, 32, 8
+
+
+def _recorder_worker(rank, world):
+    """recording.gin under data parallelism: every rank folds the squeezes of ITS shard of the dataset into fp64
+    device sums; `result()` all-reduces them (NCCL) and must give the mean over the SELECTED samples of the whole set."""
+    import greedy_multimodal_learning_b200 as pkg
+    dev = torch.device("cuda", rank)
+    p = mo.synth_params(5, REC_C, REC_C)
+    blocks = []
+    for _ in range(2):
+        m = pkg.MMTM_mitigate(REC_C, REC_C, 4)
+        with torch.no_grad():
+            for dst, src in zip((m.fc_squeeze.weight, m.fc_squeeze.bias, m.fc_visual.weight, m.fc_visual.bias,
+                                 m.fc_skeleton.weight, m.fc_skeleton.bias), p.tensors()):
+                dst.copy_(src)
+        blocks.append(m.to(dev).eval())
+    selected = [0, 2, 3, 7, 9]                      # dataset indices that count (get_rescale_weights' train_indices)
+    rec = pkg.SqueezeMeanRecorder(blocks, selected_indices=selected)
+    # uneven shards, two batches per rank; rank 1's first batch has no selected sample at all
+    shards = {0: [[0, 1, 2], [3, 4]], 1: [[5, 6], [7, 8, 9]]}[rank]
+    with torch.no_grad():
+        for batch in shards:
+            for bi, blk in enumerate(blocks):
+                x = mo.synth_inputs(40 + bi, REC_N, REC_C, REC_H)
+                blk(x["A"][batch].to(dev), x["B"][batch].to(dev), return_squeezed_mps=True)
+            rec.update(batch)
+    res = rec.result()
+    return [[v.cpu().numpy() for v in blk] for blk in res[1:]]
+
+
+def test_squeeze_mean_recorder_all_reduces_across_ranks():
+    r0, r1 = _spawn(_recorder_worker)
+    selected = [0, 2, 3, 7, 9]
+    for bi in range(2):
+        x = mo.synth_inputs(40 + bi, REC_N, REC_C, REC_H)
+        want = [x[k][selected].double().mean(dim=(2, 3)).mean(0).numpy() for k in ("A", "B")]
+        for view in range(2):
+            assert np.array_equal(r0[bi][view], r1[bi][view])              # rank-identical after the all-reduce
+            np.testing.assert_allclose(r0[bi][view], want[view], rtol=1e-6, atol=1e-7)
