@@ -74,6 +74,14 @@ VARIANTS = {
     "f_c28": (L.F_FORCE_TILE, {"tile_chunk_kb_fwd": 28}),
     "f_c56": (L.F_FORCE_TILE, {"tile_chunk_kb_fwd": 56}),
     "f_c100": (L.F_FORCE_TILE, {"tile_chunk_kb_fwd": 100}),
+    "l_cs8": (0, {"tile_kind": 2, "fused_cluster": 8}),
+    "l_cs4": (0, {"tile_kind": 2, "fused_cluster": 4}),
+    "l_occ5": (0, {"tile_kind": 2, "fused_occ": 5}),
+    "l_stash0": (0, {"tile_kind": 2, "fused_stash_kb": 0}),
+    "l_stash12": (0, {"tile_kind": 2, "fused_stash_kb": 12}),
+    "l_stash40": (0, {"tile_kind": 2, "fused_stash_kb": 40}),
+    "l_cs8_stash40": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_stash_kb": 40}),
+    "l_cs8_occ5": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_occ": 5}),
     "x_c14": (L.F_FORCE_TILE, {"tile_chunk_kb": 14}),
     "x_c56": (L.F_FORCE_TILE, {"tile_chunk_kb": 56}),
     "sw_g24": (L.F_FORCE_TILE, {"tile_gemm_ctas": 24}),
