@@ -253,7 +253,7 @@ extern int g_fused_stash_kb;
 extern int g_sq_variant;
 extern int g_tile_kind, g_tile_lag, g_tile_gemm_ctas, g_tile_m, g_tile_chunk_kb, g_tile_min_mb;
 extern long long* g_tile_stats;
-extern int g_tile_nodeps, g_tile_ksplit_tiles, g_tile_switch, g_tile_trace_only, g_tile_rpol, g_tile_max_slots, g_tile_split_copies, g_tile_draw, g_tile_chunk_kb_fwd, g_tile_min_mb_light;
+extern int g_tile_nodeps, g_tile_ksplit_tiles, g_tile_switch, g_tile_trace_only, g_tile_rpol, g_tile_max_slots, g_tile_split_copies, g_tile_draw, g_tile_chunk_kb_fwd, g_tile_min_mb_light, g_tile_wgrad;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -298,6 +298,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "tile_draw")) { g_tile_draw = value < 1 ? 1 : (value > 64 ? 64 : (int)value); return GML_OK; }
   if (!strcmp(name, "tile_chunk_kb_fwd")) { g_tile_chunk_kb_fwd = value < 1 ? 1 : (value > 100 ? 100 : (int)value); return GML_OK; }
   if (!strcmp(name, "tile_min_mb_light")) { g_tile_min_mb_light = value < 0 ? 0 : (int)value; return GML_OK; }
+  if (!strcmp(name, "tile_wgrad")) { g_tile_wgrad = value != 0; return GML_OK; }
   if (!strcmp(name, "tile_switch")) { g_tile_switch = value != 0; return GML_OK; }
   if (!strcmp(name, "sq_variant")) { g_sq_variant = (int)value & 127; return GML_OK; }
   if (!strcmp(name, "tile_min_mb")) { g_tile_min_mb = value < 0 ? 0 : (int)value; return GML_OK; }
@@ -480,10 +481,12 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
 
   // weight gradients over the whole batch (reduction over samples inside one CTA per tile or split-K
   // with an ordered fold: deterministic, no atomics)
-  bool bias_done = false;  // the tile pipeline forms the bias gradients itself
+  bool bias_done = false;   // the tile pipeline forms the bias gradients itself
+  bool wgrad_tiled = false; // ... and, when all three are requested, the weight gradients too
   auto weight_grads = [&](cudaStream_t ws_stream, void* ws_mem) -> int {
     GemmDesc gw[3];
     int cw = 0;
+    if (wgrad_tiled) return GML_OK;
     if (d_w_v) {
       if (la) gw[cw++] = GemmDesc{de_a, h, d_w_v, nullptr, nullptr, d.c_v, d.d, d.n, d.c_v, d.d, d.d, 0, 0, 0, kActNone, 0};
       else GML_TRY(launch_fill_zero(d_w_v, (size_t)d.c_v * d.d, ws_stream));
@@ -527,7 +530,7 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   if (can_tile && ((flags & GML_F_FORCE_TILE) || tile_preferred(d.n, d.c_v, d.hw_v, d.d, true))) {
     FusedBwdArgs fb{go_a, go_b, a, b, w_sq, w_v, w_s, z, h, g_a, g_b, run_v, run_s, d_a, d_b, de_a, de_b, dh,
                     d.n, d.c_v, d.hw_v, d.d, mode, gate_scale};
-    const int rc = launch_tile_bwd(fb, dz, d_b_v, d_b_s, d_b_sq, tile_ws, tile_bytes, st);
+    const int rc = launch_tile_bwd(fb, dz, d_b_v, d_b_s, d_b_sq, d_w_v, d_w_s, d_w_sq, &wgrad_tiled, tile_ws, tile_bytes, st);
     if (rc == GML_OK) { tiled = true; bias_done = true; }
     else if (rc != GML_E_UNSUPPORTED || (flags & GML_F_FORCE_TILE)) return rc;
   }

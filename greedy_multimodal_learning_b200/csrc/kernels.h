@@ -127,7 +127,7 @@ size_t tile_bwd_workspace_bytes(int n, int c, int hw, int d);
 int launch_tile_fwd(const FusedFwdArgs& args, float* gate_sum, float* run_v, float* run_s, float step, void* ws,
                     size_t ws_bytes, cudaStream_t st);
 // dz_flat: [2, N, C] scratch; d_b_*: bias gradients (column sums of dE_a, dE_b, dH) or nullptr
-int launch_tile_bwd(const FusedBwdArgs& args, float* dz_flat, float* d_b_v, float* d_b_s, float* d_b_sq, void* ws,
-                    size_t ws_bytes, cudaStream_t st);
+int launch_tile_bwd(const FusedBwdArgs& a, float* dz_flat, float* d_b_v, float* d_b_s, float* d_b_sq, float* d_w_v,
+                    float* d_w_s, float* d_w_sq, bool* wgrad_done, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace gml

@@ -57,6 +57,7 @@ int g_tile_rpol = 0;        // tunable "tile_rpol": L2 policy of the R-stage rea
 int g_tile_max_slots = 0;   // tunable "tile_max_slots": cap on the slot ring (0 = as many as fit)
 int g_tile_split_copies = 1;
 int g_tile_draw = 4;        // tunable "tile_draw": stream tickets per draw (two draws are kept in flight)
+int g_tile_wgrad = 1;       // tunable "tile_wgrad": weight-gradient GEMMs run inside the backward pipeline launch
 int g_tile_nodeps = 0;      // debug/measurement ONLY (wrong results): S items do not wait for the gates
 long long* g_tile_stats = nullptr;  // debug: per-CTA cycle breakdown (device buffer, 16 slots per CTA)
 
@@ -89,7 +90,13 @@ struct GemmStage {
   const float* bias; const float* bias2;
   const float* mask; int ldmask;     // kEpiMask: keep where mask > 0
   int epi; float div;
+  // weight-gradient ("post") stages: A is a [m_rows, K] matrix of its own (K = batch), tiled in 128 rows; output rows
+  // >= m_split go to out2 (row - m_split).  0 = a stage of the per-tile FC chain (A rows = the samples of the tile).
+  int m_rows, m_split;
 };
+
+// transpose job: out[j * ld_out + i] = in[i * ld_in + j], i < rows, j < cols (32 x 32 tiles through shared memory)
+struct TrJob { const float* in; float* out; int rows, cols, ld_in, ld_out; };
 
 struct ColItem {   // out[j] = sum_i x[i * ld + j]; optional running-mean update (balanced_mmtm.py:113-114)
   const float* x; float* out; int rows, cols, ld;
@@ -104,7 +111,14 @@ struct TileParams {
   const float* add[2];    // backward S: dZ / HW per plane (written by F2 in this launch)
   float* rout[2];         // R output per modality; forward: z + mod * C with row stride 2C; backward: dE flat
   int rout_ld;            // row stride of rout (forward 2C, backward C)
-  GemmStage st[2];
+  GemmStage st[4];          // [0], [1]: the FC chain of a tile; [2], [3]: weight gradients (backward, optional)
+  int n_post;               // 0 or 2 post stages
+  // K-major operands of the weight-gradient GEMMs (K = batch): H^T and Z^T are transposed by the otherwise idle warp 9
+  // of the stream CTAs at the start of the launch; dE^T is written by the R-stage workers next to dE, dH^T by the
+  // epilogue of the dH GEMM next to dH.  ldt = row stride of all four ([*, ldt], ldt = N rounded up to 32).
+  TrJob tr_pre[2];
+  int n_tr_pre;
+  float* de_t; float* dh_t; int ldt;
   ColItem cs[4];
   int n_cs;
   // backward prologue: transposed weights
@@ -195,7 +209,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // 
   return ok != 0;
 }
 
-struct __align__(16) SlotMeta { int kind, mod, tile, q0, rofs, pad0, pad1, pad2; };  // rofs: offset of the chunk's first R result
+struct __align__(16) SlotMeta { int kind, mod, tile, q0, rofs, sample, c0, pad2; };  // rofs: offset of the chunk's first R result
 
 __device__ __forceinline__ int tile_rows(const TileParams& P, int t) {
   const int r = P.n - t * P.m_tile;
@@ -384,10 +398,10 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
         const int nl = P.cps == 1 ? (int)ch : (int)__umulhi(ch, P.cps_magic);  // ch / cps
         SlotMeta m;
         m.kind = seg_kind; m.mod = mod; m.tile = seg_t; m.q0 = q0;
-        m.rofs = (seg_n0 + nl) * P.rout_ld + ((int)ch - nl * P.cps) * P.p;
-        m.pad0 = m.pad1 = m.pad2 = 0;
+        m.sample = seg_n0 + nl; m.c0 = ((int)ch - nl * P.cps) * P.p;
+        m.rofs = m.sample * P.rout_ld + m.c0;
         *reinterpret_cast<int4*>(&metas[slot]) = make_int4(m.kind, m.mod, m.tile, m.q0);
-        metas[slot].rofs = m.rofs;
+        *reinterpret_cast<int4*>(&metas[slot].rofs) = make_int4(m.rofs, m.sample, m.c0, 0);
       }
       __syncwarp();
       rec = (rec & ~(0xffull << (8 * slot))) |
@@ -527,8 +541,19 @@ __device__ __forceinline__ void reduce_chunk_t(const TileParams& P, const SlotMe
     }
     if (lane_in == 0 && (P.nodeps != 4 || t0 == 123.456f)) {
       if (BWD) {
-        if (act0) { const float g = sgate[pl0]; dst[pl0] = t0 * P.gate_scale * g * (1.f - g); }  // dE = dg * g (1 - g)
-        if (act1) { const float g = sgate[pl1]; dst[pl1] = t1 * P.gate_scale * g * (1.f - g); }
+        // dE = dg * g (1 - g); with the weight gradients folded in, also dE^T[channel][sample] (one 4-byte store per
+        // plane: ~N*2C stores per launch, absorbed by L2)
+        float* tdst = P.de_t ? P.de_t + (size_t)(m.mod * P.c + m.c0) * P.ldt + m.sample : nullptr;
+        if (act0) {
+          const float g = sgate[pl0]; const float v = t0 * P.gate_scale * g * (1.f - g);
+          dst[pl0] = v;
+          if (tdst) tdst[(size_t)pl0 * P.ldt] = v;
+        }
+        if (act1) {
+          const float g = sgate[pl1]; const float v = t1 * P.gate_scale * g * (1.f - g);
+          dst[pl1] = v;
+          if (tdst) tdst[(size_t)pl1 * P.ldt] = v;
+        }
       } else {
         if (act0) dst[pl0] = t0 / (float)hw;   // squeeze
         if (act1) dst[pl1] = t1 / (float)hw;
@@ -667,7 +692,7 @@ __device__ __forceinline__ void gemm_item_mainloop(const TileParams& P, const Ge
                                                    unsigned char* u_smem, const GemmBars& bars, uint32_t tmem,
                                                    uint32_t kbase, uint32_t gbase, int nk, float (&sum)[64], int warp,
                                                    int lane, int tid, long long* dbg) {  // (kbase, gbase, nk by value)
-  const int m0 = it.tile * P.m_tile;
+  const int m0 = g.m_rows ? it.tile * UM : it.tile * P.m_tile;
   const int n0 = it.ntile * UN;
   const int k_begin = it.split * g.k_per_split;
   if (warp >= U_PRODUCERS / 32) {
@@ -795,30 +820,50 @@ __device__ __forceinline__ void gemm_stage_tile(float* tile, const float (&sum)[
 }
 
 __device__ __noinline__ void gemm_store_rows(const TileParams& P, const GemmStage& g, int tile_idx, int ntile,
-                                             const float* tile, int warp, int lane) {
-  const int m0 = tile_idx * P.m_tile, rows = tile_rows(P, tile_idx);
+                                             float* tile, int warp, int lane, float* out_t, int ldt) {
+  const int m0 = g.m_rows ? tile_idx * UM : tile_idx * P.m_tile;
+  const int rows = g.m_rows ? min(UM, g.m_rows - m0) : tile_rows(P, tile_idx);
   const int col = ntile * UN + 4 * lane;
-  if (col >= g.n_total) return;
-  const bool hi = col >= g.n_split;
-  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (g.bias) bias = __ldg(reinterpret_cast<const float4*>(hi ? g.bias2 + (col - g.n_split) : g.bias + col));
-  float* obase = hi ? g.out2 + (col - g.n_split) : g.out + col;
-  const int epi = g.epi;
-  const float div = g.div;
-  for (int r = warp; r < rows; r += U_PRODUCERS / 32) {
-    float4 v = *reinterpret_cast<const float4*>(tile + (size_t)r * kTilePitch + 4 * lane);
-    v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-    if (epi == kEpiRelu) {
-      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-    } else if (epi == kEpiSigmoid) {
-      v.x = sigmoidf_fast(v.x); v.y = sigmoidf_fast(v.y); v.z = sigmoidf_fast(v.z); v.w = sigmoidf_fast(v.w);
-    } else if (epi == kEpiMask) {
-      const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + (size_t)(m0 + r) * g.ldmask + col));
-      v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
-    } else {
-      v.x = v.x / div; v.y = v.y / div; v.z = v.z / div; v.w = v.w / div;
+  if (col < g.n_total) {
+    const bool hi = col >= g.n_split;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.bias) bias = __ldg(reinterpret_cast<const float4*>(hi ? g.bias2 + (col - g.n_split) : g.bias + col));
+    float* obase = hi ? g.out2 + (col - g.n_split) : g.out + col;
+    const int epi = g.epi;
+    const float div = g.div;
+    for (int r = warp; r < rows; r += U_PRODUCERS / 32) {
+      float4 v = *reinterpret_cast<const float4*>(tile + (size_t)r * kTilePitch + 4 * lane);
+      v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+      if (epi == kEpiRelu) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      } else if (epi == kEpiSigmoid) {
+        v.x = sigmoidf_fast(v.x); v.y = sigmoidf_fast(v.y); v.z = sigmoidf_fast(v.z); v.w = sigmoidf_fast(v.w);
+      } else if (epi == kEpiMask) {
+        const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + (size_t)(m0 + r) * g.ldmask + col));
+        v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+      } else {
+        v.x = v.x / div; v.y = v.y / div; v.z = v.z / div; v.w = v.w / div;
+      }
+      const int gr = m0 + r;
+      float* o = (g.m_split && gr >= g.m_split) ? g.out2 + (size_t)(gr - g.m_split) * g.ldo + col
+                                                : obase + (size_t)gr * g.ldo;
+      *reinterpret_cast<float4*>(o) = v;
+      if (out_t) *reinterpret_cast<float4*>(tile + (size_t)r * kTilePitch + 4 * lane) = v;  // final value for the pass below
     }
-    *reinterpret_cast<float4*>(obase + (size_t)(m0 + r) * g.ldo) = v;
+  }
+  if (out_t) {
+    // K-major copy for the weight-gradient GEMMs: out_t[column][sample].  Column j of the staged tile goes out as one
+    // run of `rows` consecutive floats (the eight worker warps take columns j = warp, warp + 8, ...).
+    asm volatile("bar.sync 1, %0;" ::"n"(U_PRODUCERS) : "memory");
+    const int ncols = min(UN, g.n_total - ntile * UN);
+    for (int j = warp; j < ncols; j += U_PRODUCERS / 32) {
+      float* dst = out_t + (size_t)(ntile * UN + j) * ldt + m0;
+#pragma unroll
+      for (int q = 0; q < UM / 32; ++q) {
+        const int r = lane + 32 * q;
+        if (r < rows) dst[r] = tile[(size_t)r * kTilePitch + j];
+      }
+    }
   }
 }
 
@@ -846,6 +891,38 @@ __device__ void transpose_weights(const TileParams& P, int grank, float* scratch
 #pragma unroll 8
     for (int i = 0; i < 32; ++i) out[(size_t)(c0 + i) * ld_out + out_col_off + r0 + lane] = s[lane][i];
     __syncwarp();
+  }
+}
+
+// Generic 32 x 32 transposes (any rows / cols) by ONE warp per party: the tiles of all jobs form one index space, party
+// `part` of `nparts` takes every nparts-th tile.  All 32 row loads of a tile are issued before the first one is used:
+// while the stream CTAs saturate HBM a load takes several microseconds, so the depth in flight is what counts.
+// Used to give the weight-gradient GEMMs K-major operands: dW = X^T Y reduces over the batch, and a TF32 UMMA operand
+// must have its reduction dimension contiguous.
+__device__ void transpose_jobs_warp(const TrJob* jobs, int njobs, int part, int nparts, float (*s)[33], int lane) {
+  int base = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const TrJob& t = jobs[j];
+    const int tr = (t.rows + 31) / 32, tc = (t.cols + 31) / 32, total = tr * tc;
+    int first = (part - base) % nparts;
+    if (first < 0) first += nparts;
+    for (int tile = first; tile < total; tile += nparts) {
+      const int r0 = (tile / tc) * 32, c0 = (tile % tc) * 32;
+      const bool cin = c0 + lane < t.cols;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        v[i] = (cin && r0 + i < t.rows) ? __ldcg(t.in + (size_t)(r0 + i) * t.ld_in + c0 + lane) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s[i][lane] = v[i];
+      __syncwarp();
+      const bool rout = r0 + lane < t.rows;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i)
+        if (rout && c0 + i < t.cols) t.out[(size_t)(c0 + i) * t.ld_out + r0 + lane] = s[lane][i];
+      __syncwarp();
+    }
+    base += total;
   }
 }
 
@@ -922,7 +999,14 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
   int cs_blocks[5];
   cs_blocks[0] = 0;
   for (int i = 0; i < 4; ++i) cs_blocks[i + 1] = cs_blocks[i] + (i < P.n_cs ? (P.cs[i].cols + 31) / 32 : 0);
-  const unsigned total = per_tile * (unsigned)T + (unsigned)cs_blocks[4];
+  // ticket space: [FC chain items of every tile][column sums][weight-gradient GEMM items]
+  const unsigned t_cs = per_tile * (unsigned)T, t_post = t_cs + (unsigned)cs_blocks[4];
+  unsigned post_items[2] = {0u, 0u};
+  if (P.n_post) {
+    post_items[0] = (unsigned)(((P.st[2].m_rows + UM - 1) / UM) * P.st[2].n_tiles);
+    post_items[1] = (unsigned)(((P.st[3].m_rows + UM - 1) / UM) * P.st[3].n_tiles);
+  }
+  const unsigned total = t_post + post_items[0] + post_items[1];
   uint32_t kbase = 0, gbase = 0;
   float sum[64];
   long long c_dep = 0, c_main = 0, c_epi = 0, n_items = 0, c_e[4] = {0, 0, 0, 0};
@@ -933,7 +1017,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     __syncthreads();
     const unsigned ticket = s_ticket;
     if (ticket >= total || P.nodeps >= 5) break;
-    if (ticket >= per_tile * (unsigned)T) {
+    if (ticket >= t_cs && ticket < t_post) {
       // ---- column-sum item: needs every tile's R, F1 and F2 -----------------------------------------------------
       if (tid == 0) {
         for (int t = 0; t < T; ++t) {
@@ -944,25 +1028,45 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
         }
       }
       __syncthreads();
-      int blk = (int)(ticket - per_tile * (unsigned)T), which = 0;
+      int blk = (int)(ticket - t_cs), which = 0;
       while (which < 3 && blk >= cs_blocks[which + 1]) ++which;
       colsum_item(P.cs[which], blk - cs_blocks[which], reinterpret_cast<float*>(u_smem), tid);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // scratch is a later item's TMA destination
       continue;
     }
     GemmItem it;
-    it.tile = (int)(ticket / per_tile);
-    const int r = (int)(ticket - (unsigned)it.tile * per_tile);
-    it.stage = r >= i1 ? 1 : 0;
+    int r;
+    if (ticket >= t_post) {   // weight-gradient item: (m-tile, n-tile) of post stage 2 or 3
+      unsigned q = ticket - t_post;
+      it.stage = q >= post_items[0] ? 3 : 2;
+      if (it.stage == 3) q -= post_items[0];
+      it.tile = (int)(q / (unsigned)P.st[it.stage].n_tiles);
+      r = (int)(q - (unsigned)it.tile * (unsigned)P.st[it.stage].n_tiles);
+    } else {
+      it.tile = (int)(ticket / per_tile);
+      r = (int)(ticket - (unsigned)it.tile * per_tile);
+      it.stage = r >= i1 ? 1 : 0;
+      if (it.stage) r -= i1;
+    }
     const GemmStage& g = P.st[it.stage];
-    const int rr = it.stage ? r - i1 : r;
+    const int rr = r;
     it.ntile = rr / g.splits;
     it.split = rr - it.ntile * g.splits;
-    unsigned* tc = tile_ctr(P, it.tile);
+    unsigned* tc = tile_ctr(P, it.stage < 2 ? it.tile : 0);
     const long long tg0 = timing ? clk() : 0;
     const unsigned long long t_item0 = (tid == 0 && P.stats) ? global_ns() : 0ull;
     if (tid == 0) {
       if (P.w_cat_t) wait_counter(&P.ctr[3], (unsigned)P.n_gemm);
-      if (it.stage == 0) {
+      if (it.stage >= 2) {
+        // dE^T is complete with every tile's R stage, dH^T with every tile's dH GEMM, H^T / Z^T when every original
+        // stream CTA's warp 9 has reported
+        for (int t = 0; t < T; ++t) {
+          const unsigned rneed = 2u * (unsigned)((size_t)tile_rows(P, t) * P.c / P.p);
+          wait_counter(tile_ctr(P, t) + 0, rneed);
+          wait_counter(tile_ctr(P, t) + 1, (unsigned)P.st[0].n_tiles);
+        }
+        wait_counter(&P.ctr[4], gridDim.x - (unsigned)P.n_gemm);
+      } else if (it.stage == 0) {
         const unsigned rneed = 2u * (unsigned)((size_t)tile_rows(P, it.tile) * P.c / P.p);  // one per R item
         wait_counter(tc + 0, rneed);
         // the partial planes of this ring position were last used by tile - kRingTiles: fully folded?
@@ -1028,7 +1132,9 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     if (finish) {
       if (warp < 8) gemm_stage_tile(reinterpret_cast<float*>(u_smem), sum, warp, lane);
       __syncthreads();
-      if (warp < 8) gemm_store_rows(P, g, it.tile, it.ntile, reinterpret_cast<const float*>(u_smem), warp, lane);
+      if (warp < 8)
+        gemm_store_rows(P, g, it.tile, it.ntile, reinterpret_cast<float*>(u_smem), warp, lane,
+                        (it.stage == 0 && P.dh_t) ? P.dh_t : nullptr, P.ldt);
       // the staged tile lives in the operand stages: order these generic accesses before the next item's TMA writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tg4 = (timing || timing2) ? clk() : 0;
@@ -1040,7 +1146,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
         if (tid == 128) { st_cycles[12] += tg4 - tg3; st_cycles[13] += tg5 - tg4; }
         else { st_cycles[14] += tg5 - tg4; st_cycles[15] += t6 - tg5; }
       }
-      if (tid == 0) red_release_add(tc + 1 + it.stage, 1u);
+      if (tid == 0 && it.stage < 2) red_release_add(tc + 1 + it.stage, 1u);
       if (tid == 0 && P.stats && ticket < 256) P.stats[(size_t)(kTraceGemmRow + ticket) * 16 + 7] = (long long)global_ns();
     }
     if (timing) {
@@ -1067,6 +1173,7 @@ __global__ void __launch_bounds__(kThreads, 1) tile_pipeline_kernel(const __grid
   __shared__ unsigned s_role;
   __shared__ __align__(8) uint64_t s_full[kMaxSlots], s_empty[kMaxSlots];
   __shared__ SlotMeta s_meta[kMaxSlots];
+  __shared__ float s_tr[32][33];
   const int tid = threadIdx.x;
   if (tid == 0) s_role = atomicAdd(&P.ctr[2], 1u);
   __syncthreads();
@@ -1092,7 +1199,14 @@ __global__ void __launch_bounds__(kThreads, 1) tile_pipeline_kernel(const __grid
   __syncthreads();
   StreamSmem sm{smem, P.slot_bytes, P.chunk_bytes, P.p};
   if (tid >= U_PRODUCERS + 32) {
-    // (warp 9 has no job in the stream role)
+    // warp 9 has no part in streaming: in the CTAs that started in the stream role it transposes H and Z for the
+    // weight-gradient GEMMs (no dependencies: forward results), one 32 x 32 tile at a time, then reports
+    if (P.n_tr_pre && role >= P.n_gemm) {
+      transpose_jobs_warp(P.tr_pre, P.n_tr_pre, role - P.n_gemm, (int)gridDim.x - P.n_gemm, s_tr, tid & 31);
+      __threadfence();
+      __syncwarp();
+      if ((tid & 31) == 0) red_release_add(&P.ctr[4], 1u);
+    }
   } else if (tid >= U_PRODUCERS) {
     stream_loader(P, sm, s_meta, s_full, s_empty, st_cycles, tid & 31);
   } else {
@@ -1154,7 +1268,7 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   f.nbuf = bwd ? 2 : 1;
   f.slot_bytes = (uint32_t)round_up((size_t)f.nbuf * f.chunk_bytes + 2 * (size_t)f.p * 4, 128);
   const size_t gemm_smem = (size_t)USTAGES * U_STAGE_BYTES;
-  const size_t budget = 224 * 1024 - 1024;
+  const size_t budget = 218 * 1024;  // 227 KB - static shared memory (5 KB) - alignment slack - 1 KB header
   int slots = (int)(budget / f.slot_bytes);
   if (slots < 2) return false;
   slots = slots >= 8 ? 8 : (slots >= 4 ? 4 : 2);  // a power of two; a group of warps owns two slots
@@ -1174,7 +1288,7 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   if (m < 1) m = 1;
   f.m_tile = (int)m;
   f.n_tiles = (n + f.m_tile - 1) / f.m_tile;
-  f.lag = g_tile_lag > 0 ? g_tile_lag : 6;
+  f.lag = g_tile_lag > 0 ? g_tile_lag : 8;  // all R stages first when there are <= 8 tiles: measured best (profiles/r2_sweep.md)
   if (f.lag > f.n_tiles) f.lag = f.n_tiles;
   // GEMM stages: forward (K = 2C -> N = D), (K = D -> N = 2C); backward (K = 2C -> N = D), (K = D -> N = 2C)
   const int kk[2] = {2 * c, d}, nn[2] = {d, 2 * c};
@@ -1195,12 +1309,14 @@ bool make_tile_cfg(int n, int c, int hw, int d, bool bwd, TileCfg* o) {
   // GEMM CTAs: k-tile units of one tile x ~0.6 us each, against the tile's streaming time at ~6.5 TB/s
   int g = g_tile_gemm_ctas;
   if (g <= 0) {
-    // The 3xTF32 FC work of a tile grows with C^2 while its bytes grow with C: measured best on B200 (profiles/
-    // r2_sweep.md) 48 CTAs for C = 512, 12 for 256, 3-4 for 128 -- i.e. ~C*D/5500 -- in both directions.
+    // The 3xTF32 FC work of a tile grows with C^2 while its bytes grow with C.  Measured best on B200 with GEMM CTAs
+    // that join the stream role afterwards (profiles/r2_sweep.md): forward 16 CTAs for C = 256, 48-56 for 512, i.e.
+    // ~C*D / 4096; the backward also runs the weight-gradient GEMMs and wants ~C*D / 3277 (20 and 64).
     (void)units; (void)items;
-    g = (int)((double)c * d / 5461.0 + 0.5);
+    const bool fold = bwd && g_tile_wgrad;
+    g = (int)((double)c * d / (fold ? 3277.0 : 4096.0) + 0.5);
     if (g < 3) g = 3;
-    if (g > 56) g = 56;
+    if (g > (fold ? 64 : 56)) g = fold ? 64 : 56;
   }
   const int sms = sm_count();
   if (g > sms / 2) g = sms / 2;
@@ -1252,14 +1368,15 @@ void fill_common(TileParams& P, const TileCfg& f, int n, int c, int hw, int d, b
   P.ctr = reinterpret_cast<unsigned*>(ws);
   P.part = reinterpret_cast<float*>(static_cast<char*>(ws) + f.ctr_bytes);
   P.part_tile_floats = f.part_tile_floats;
-  for (int s = 0; s < 2; ++s) {
-    P.st[s].n_tiles = f.nt[s]; P.st[s].splits = f.splits[s]; P.st[s].k_per_split = f.kps[s];
-    P.st[s].k_split = 0;
+  for (int s = 0; s < 4; ++s) {
+    P.st[s].n_tiles = s < 2 ? f.nt[s] : 0; P.st[s].splits = s < 2 ? f.splits[s] : 1; P.st[s].k_per_split = s < 2 ? f.kps[s] : 0;
+    P.st[s].k_split = 0; P.st[s].m_rows = 0; P.st[s].m_split = 0;
     P.st[s].b_box_rows = 128;
     P.st[s].out2 = nullptr; P.st[s].bias = nullptr; P.st[s].bias2 = nullptr; P.st[s].mask = nullptr; P.st[s].ldmask = 0;
     P.st[s].div = 1.f;
   }
   P.n_cs = 0;
+  P.n_post = 0; P.n_tr_pre = 0; P.de_t = nullptr; P.dh_t = nullptr; P.ldt = 0;
   P.stats = g_tile_stats;
   P.nodeps = g_tile_nodeps;
   P.gemm_joins_stream = g_tile_switch;
@@ -1319,6 +1436,12 @@ bool tile_preferred(int n, int c, int hw, int d, bool bwd) {
   return !bwd && u >= ((size_t)g_tile_min_mb_light << 20);
 }
 
+// K-major copies for the weight-gradient GEMMs: H^T, dH^T [D, ldT] and Z^T, dE^T [2C, ldT], ldT = N rounded up to 32
+static size_t tile_wgrad_bytes(int n, int c, int d) {
+  const size_t ldt = round_up((size_t)n, 32);
+  return 2 * round_up((size_t)d * ldt * 4, 256) + 2 * round_up((size_t)2 * c * ldt * 4, 256);
+}
+
 size_t tile_fwd_workspace_bytes(int n, int c, int hw, int d) {
   TileCfg f;
   if (!make_tile_cfg(n, c, hw, d, false, &f)) return 0;
@@ -1328,7 +1451,7 @@ size_t tile_fwd_workspace_bytes(int n, int c, int hw, int d) {
 size_t tile_bwd_workspace_bytes(int n, int c, int hw, int d) {
   TileCfg f;
   if (!make_tile_cfg(n, c, hw, d, true, &f)) return 0;
-  return f.ctr_bytes + f.part_bytes + 2 * round_up((size_t)2 * c * d * 4, 256) + 256;
+  return f.ctr_bytes + f.part_bytes + 2 * round_up((size_t)2 * c * d * 4, 256) + tile_wgrad_bytes(n, c, d) + 256;
 }
 
 int launch_tile_fwd(const FusedFwdArgs& a, float* gate_sum, float* run_v, float* run_s, float step, void* ws,
@@ -1368,12 +1491,13 @@ int launch_tile_fwd(const FusedFwdArgs& a, float* gate_sum, float* run_v, float*
   return launch_pipeline(P, f, kTagFusedFwd, st);
 }
 
-int launch_tile_bwd(const FusedBwdArgs& a, float* dz_flat, float* d_b_v, float* d_b_s, float* d_b_sq, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
+int launch_tile_bwd(const FusedBwdArgs& a, float* dz_flat, float* d_b_v, float* d_b_s, float* d_b_sq, float* d_w_v,
+                    float* d_w_s, float* d_w_sq, bool* wgrad_done, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (wgrad_done) *wgrad_done = false;
   TileCfg f;
   if (!make_tile_cfg(a.n, a.c, a.hw, a.d, true, &f)) return GML_E_UNSUPPORTED;
   const size_t wt = round_up((size_t)2 * a.c * a.d * 4, 256);
-  if (!ws || ws_bytes < f.ctr_bytes + f.part_bytes + 2 * wt) return GML_E_WORKSPACE;
+  if (!ws || ws_bytes < f.ctr_bytes + f.part_bytes + 2 * wt + tile_wgrad_bytes(a.n, a.c, a.d)) return GML_E_WORKSPACE;
   const void* al[] = {a.go_a, a.go_b, a.a, a.b, a.d_a, a.d_b, a.w_sq, a.w_v, a.w_s, a.h, a.g_a, a.g_b, a.de_a, a.de_b,
                       a.dh, dz_flat, ws};
   for (const void* p : al)
@@ -1413,7 +1537,44 @@ int launch_tile_bwd(const FusedBwdArgs& a, float* dz_flat, float* d_b_v, float* 
   if (d_b_s) P.cs[ncs++] = ColItem{a.de_b, d_b_s, a.n, a.c, a.c, nullptr, nullptr, 1.f, 0.f};
   if (d_b_sq) P.cs[ncs++] = ColItem{a.dh, d_b_sq, a.n, a.d, a.d, nullptr, nullptr, 1.f, 0.f};
   P.n_cs = ncs;
-  return launch_pipeline(P, f, kTagFusedBwd, st);
+  // Weight gradients inside the same launch: dW_v | dW_s = dE^T H and dW_sq = dH^T Z reduce over the batch, so their
+  // operands need K-major copies (see TileParams); the GEMM CTAs then run them as ordinary 128 x 128 items once the last
+  // tile's chain is done, while the stream CTAs are still busy with the S stage.
+  const bool fold = g_tile_wgrad && d_w_v && d_w_s && d_w_sq && a.z && aligned16(d_w_v) && aligned16(d_w_s) &&
+                    aligned16(d_w_sq) && aligned16(a.z);
+  if (fold) {
+    const int ldt = (int)round_up((size_t)a.n, 32);
+    char* tp = wp + 2 * wt;
+    float* h_t = reinterpret_cast<float*>(tp);  tp += round_up((size_t)a.d * ldt * 4, 256);
+    float* dh_t = reinterpret_cast<float*>(tp); tp += round_up((size_t)a.d * ldt * 4, 256);
+    float* z_t = reinterpret_cast<float*>(tp);  tp += round_up((size_t)2 * a.c * ldt * 4, 256);
+    float* de_t = reinterpret_cast<float*>(tp);
+    P.tr_pre[0] = TrJob{a.h, h_t, a.n, a.d, a.d, ldt};
+    P.tr_pre[1] = TrJob{a.z, z_t, a.n, 2 * a.c, 2 * a.c, ldt};
+    P.n_tr_pre = 2;
+    P.de_t = de_t; P.dh_t = dh_t; P.ldt = ldt;
+    const int kps = (int)round_up((size_t)a.n, UK);
+    GemmStage& s2 = P.st[2];   // [dW_v ; dW_s] = dE^T H      ([2C, N] x [N, D])
+    GML_TRY(make_map(&s2.tm_a, de_t, 2 * a.c, a.n, ldt, 128));
+    GML_TRY(make_map(&s2.tm_b, h_t, a.d, a.n, ldt, a.d % 128 == 0 ? 128 : 32));
+    s2.tm_a2 = s2.tm_a; s2.tm_b2 = s2.tm_b;
+    s2.m_rows = 2 * a.c; s2.m_split = a.c; s2.n_split = a.d; s2.n_total = a.d; s2.k_total = a.n;
+    s2.b_box_rows = a.d % 128 == 0 ? 128 : 32;
+    s2.n_tiles = (a.d + UN - 1) / UN; s2.splits = 1; s2.k_per_split = kps;
+    s2.out = d_w_v; s2.out2 = d_w_s; s2.ldo = a.d; s2.epi = kEpiDiv; s2.div = 1.f;
+    GemmStage& s3 = P.st[3];   // dW_sq = dH^T Z             ([D, N] x [N, 2C])
+    GML_TRY(make_map(&s3.tm_a, dh_t, a.d, a.n, ldt, 128));
+    GML_TRY(make_map(&s3.tm_b, z_t, 2 * a.c, a.n, ldt, (2 * a.c) % 128 == 0 ? 128 : 32));
+    s3.tm_a2 = s3.tm_a; s3.tm_b2 = s3.tm_b;
+    s3.m_rows = a.d; s3.m_split = 0; s3.n_split = 2 * a.c; s3.n_total = 2 * a.c; s3.k_total = a.n;
+    s3.b_box_rows = (2 * a.c) % 128 == 0 ? 128 : 32;
+    s3.n_tiles = (2 * a.c + UN - 1) / UN; s3.splits = 1; s3.k_per_split = kps;
+    s3.out = d_w_sq; s3.out2 = nullptr; s3.ldo = 2 * a.c; s3.epi = kEpiDiv; s3.div = 1.f;
+    P.n_post = 2;
+  }
+  const int rc = launch_pipeline(P, f, kTagFusedBwd, st);
+  if (rc == GML_OK && wgrad_done) *wgrad_done = fold;
+  return rc;
 }
 
 }  // namespace gml

@@ -82,6 +82,22 @@ VARIANTS = {
     "l_stash40": (0, {"tile_kind": 2, "fused_stash_kb": 40}),
     "l_cs8_stash40": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_stash_kb": 40}),
     "l_cs8_occ5": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_occ": 5}),
+    "g_lag5": (L.F_FORCE_TILE, {"tile_lag": 5}),
+    "g_lag6": (L.F_FORCE_TILE, {"tile_lag": 6}),
+    "g_lag7": (L.F_FORCE_TILE, {"tile_lag": 7}),
+    "g_lag8": (L.F_FORCE_TILE, {"tile_lag": 8}),
+    "g_lag8_m64": (L.F_FORCE_TILE, {"tile_lag": 8, "tile_m": 64}),
+    "g_lag16_m64": (L.F_FORCE_TILE, {"tile_lag": 16, "tile_m": 64}),
+    "g_lag12_m64": (L.F_FORCE_TILE, {"tile_lag": 12, "tile_m": 64}),
+    "w_nofold": (0, {"tile_wgrad": 0}),
+    "w_g16": (0, {"tile_gemm_ctas": 16}),
+    "w_g20": (0, {"tile_gemm_ctas": 20}),
+    "w_g24": (0, {"tile_gemm_ctas": 24}),
+    "w_g32": (0, {"tile_gemm_ctas": 32}),
+    "w_g40": (0, {"tile_gemm_ctas": 40}),
+    "w_g56": (0, {"tile_gemm_ctas": 56}),
+    "w_g64": (0, {"tile_gemm_ctas": 64}),
+    "w_g72": (0, {"tile_gemm_ctas": 72}),
     "x_c14": (L.F_FORCE_TILE, {"tile_chunk_kb": 14}),
     "x_c56": (L.F_FORCE_TILE, {"tile_chunk_kb": 56}),
     "sw_g24": (L.F_FORCE_TILE, {"tile_gemm_ctas": 24}),
@@ -274,7 +290,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, "tile_switch": 1, "tile_rpol": 0, "tile_max_slots": 0, "tile_split_copies": 1, "tile_draw": 4, "tile_chunk_kb_fwd": 56, "tile_min_mb_light": 190, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, "tile_switch": 1, "tile_rpol": 0, "tile_max_slots": 0, "tile_split_copies": 1, "tile_draw": 4, "tile_chunk_kb_fwd": 56, "tile_min_mb_light": 190, "tile_wgrad": 1, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 # workspace sizes depend on the tile tunables: re-query for this variant
                 b.ws_bytes = lib.gml_mmtm_bwd_workspace_bytes(b.dims)
