@@ -250,10 +250,11 @@ extern long long* g_gemm_trace;
 extern int g_fused_weight_ratio_x100;
 extern int g_fused_group_kb;
 extern int g_fused_stash_kb;
+extern int g_fused_wsmem;
 extern int g_sq_variant;
 extern int g_tile_kind, g_tile_lag, g_tile_gemm_ctas, g_tile_m, g_tile_chunk_kb, g_tile_min_mb;
 extern long long* g_tile_stats;
-extern int g_tile_nodeps, g_tile_ksplit_tiles, g_tile_switch, g_tile_trace_only, g_tile_rpol, g_tile_max_slots, g_tile_split_copies, g_tile_draw, g_tile_chunk_kb_fwd, g_tile_min_mb_light, g_tile_wgrad;
+extern int g_tile_nodeps, g_tile_ksplit_tiles, g_tile_switch, g_tile_trace_only, g_tile_rpol, g_tile_max_slots, g_tile_split_copies, g_tile_draw, g_tile_chunk_kb_fwd, g_tile_min_mb_light, g_tile_wgrad, g_tile_light_fwd;
 }
 extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!name) return GML_E_BADARG;
@@ -268,6 +269,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   }
   if (!strcmp(name, "fused_weight_ratio_x100")) { g_fused_weight_ratio_x100 = (int)value; return GML_OK; }
   if (!strcmp(name, "overlap_wgrad")) { g_overlap_wgrad.store(value ? 1 : 0); return GML_OK; }
+  if (!strcmp(name, "fused_wsmem")) { g_fused_wsmem = value < 0 ? -1 : (int)(value & 3); return GML_OK; }
   if (!strcmp(name, "fused_stash_kb")) { g_fused_stash_kb = value < 0 ? 0 : (value > 200 ? 200 : (int)value); return GML_OK; }
   if (!strcmp(name, "fused_group_kb")) { g_fused_group_kb = (int)value; return GML_OK; }
   if (!strcmp(name, "gemm_big_tiles")) { g_gemm_big_tiles = value ? 1 : 0; return GML_OK; }
@@ -298,6 +300,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "tile_draw")) { g_tile_draw = value < 1 ? 1 : (value > 64 ? 64 : (int)value); return GML_OK; }
   if (!strcmp(name, "tile_chunk_kb_fwd")) { g_tile_chunk_kb_fwd = value < 1 ? 1 : (value > 100 ? 100 : (int)value); return GML_OK; }
   if (!strcmp(name, "tile_min_mb_light")) { g_tile_min_mb_light = value < 0 ? 0 : (int)value; return GML_OK; }
+  if (!strcmp(name, "tile_light_fwd")) { g_tile_light_fwd = value != 0; return GML_OK; }
   if (!strcmp(name, "tile_wgrad")) { g_tile_wgrad = value != 0; return GML_OK; }
   if (!strcmp(name, "tile_switch")) { g_tile_switch = value != 0; return GML_OK; }
   if (!strcmp(name, "sq_variant")) { g_sq_variant = (int)value & 127; return GML_OK; }

@@ -27,6 +27,8 @@
 
 #include <map>
 #include <mutex>
+#include <cstdio>
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -42,6 +44,8 @@ int g_fused_kind = 0;      // 0 auto, 1 shared-memory resident, 2 L2 resident
 int g_fused_occ = 4;       // L2-resident kernels: CTAs per SM the register budget is compiled for (4: 64 regs, 5: 48)
 int g_fused_group_kb = 128;  // L2-resident kernels: take 2 samples per cluster while 2 slices <= this many KB per CTA
 int g_fused_stash_kb = 24; // L2-resident kernels: shared memory per CTA used to stash planes between the passes (24 KB measured best; 46+ costs occupancy)
+int g_fused_wsmem = -1;    // L2-resident kernels: FC weight slices prefetched into shared memory (cp.async, hidden behind pass 1);
+                           // -1 auto (whatever fits at 4 CTAs per SM), else bit 0 = first FC, bit 1 = second FC
 int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch look-ahead distance in groups (0 = off)
 long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
@@ -66,6 +70,7 @@ struct FusedCfg {
   int prefetch;      // L2-resident kernels: issue bulk L2 prefetches of the CTA's planes up front
   int trace_first;   // first CTA of the traced window (L2-resident kernels)
   int keep_planes;   // L2-resident kernels: the first keep_planes planes of a CTA are stashed in shared memory
+  int wsm;           // L2-resident kernels: bit 0 / bit 1 = weight slice of the first / second FC lives in shared memory
 };
 
 #define GML_STAMP(k)                                                                       \
@@ -195,7 +200,7 @@ __device__ __forceinline__ void plane_drained(const FusedCfg& f, const Smem& s, 
 // y[row] = <W[row0 + row, 0:K], x[g, 0:K]>, K % 4 == 0.  Each warp owns kRowsPerBatch rows at a time
 // and issues all their weight loads before the first FMA (the weights come from L2: the cost is
 // latency, so several rows must be in flight); lane r then finishes row r.
-template <int T, int GMAX, int R, typename RowPtr, typename Epi>
+template <int T, int GMAX, int R, bool SM, typename RowPtr, typename Epi>
 __device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
                                             Epi epi) {
   constexpr int kWarps = T / 32;
@@ -213,7 +218,8 @@ __device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, con
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int row = min(base + r, nrows - 1);  // clamp: duplicates are discarded in the epilogue
-        wv[r] = __ldg(reinterpret_cast<const float4*>(rowptr(row)) + i);
+        wv[r] = SM ? *(reinterpret_cast<const float4*>(rowptr(row)) + i)
+                   : __ldg(reinterpret_cast<const float4*>(rowptr(row)) + i);
       }
 #pragma unroll
       for (int g = 0; g < GMAX; ++g) {
@@ -237,18 +243,19 @@ __device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, con
   }
 }
 
-template <int T, int GMAX, typename RowPtr, typename Epi>
+// SM: the rows live in shared memory (plain loads) instead of global memory (ld.global.nc)
+template <int T, int GMAX, bool SM = false, typename RowPtr, typename Epi>
 __device__ __forceinline__ void gemv_rows(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
                                           Epi epi) {
   // few rows: spread them over more warps (one L2 round trip either way)
-  if (nrows <= (T / 32)) gemv_rows_r<T, GMAX, 1>(rowptr, nrows, k, x, ldx, gcount, epi);
-  else if (nrows <= 2 * (T / 32)) gemv_rows_r<T, GMAX, 2>(rowptr, nrows, k, x, ldx, gcount, epi);
-  else gemv_rows_r<T, GMAX, kRowsPerBatch>(rowptr, nrows, k, x, ldx, gcount, epi);
+  if (nrows <= (T / 32)) gemv_rows_r<T, GMAX, 1, SM>(rowptr, nrows, k, x, ldx, gcount, epi);
+  else if (nrows <= 2 * (T / 32)) gemv_rows_r<T, GMAX, 2, SM>(rowptr, nrows, k, x, ldx, gcount, epi);
+  else gemv_rows_r<T, GMAX, kRowsPerBatch, SM>(rowptr, nrows, k, x, ldx, gcount, epi);
 }
 
 // y[col] = sum_k x[g, k] * W[k, col0 + col] (transposed GEMV): thread = (k-slice, col), coalesced in
 // col.  Partials are ADDED into s_part[slice][g][col]; the caller reduces the slices in a fixed order.
-template <int T, int GMAX>
+template <int T, int GMAX, bool SM = false>
 __device__ __forceinline__ void gemv_cols_partial(const float* __restrict__ w, int ldw, int col0, int ncols, int k0,
                                                   int k1, const float* x, int ldx, int gcount, float* s_part) {
   const int slices = T / ncols;
@@ -261,7 +268,7 @@ __device__ __forceinline__ void gemv_cols_partial(const float* __restrict__ w, i
   const float* wp = w + col0 + col;
 #pragma unroll 16
   for (int kk = ka; kk < kb; ++kk) {
-    const float wv = __ldg(wp + (size_t)kk * ldw);
+    const float wv = SM ? wp[(size_t)kk * ldw] : __ldg(wp + (size_t)kk * ldw);
 #pragma unroll
     for (int g = 0; g < GMAX; ++g)
       if (g < gcount) acc[g] = fmaf(x[(size_t)g * ldx + kk], wv, acc[g]);
@@ -622,6 +629,7 @@ bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out
   f.trace_first = 0;
   f.prefetch = 0;
   f.keep_planes = 0;
+  f.wsm = 0;
   const size_t total = f.data_bytes + extras_bytes(f, true);
   if (total > (cs == 4 ? 232448u : 115000u)) return false;
   *out = f;
@@ -725,9 +733,17 @@ __host__ __device__ inline size_t l2_small_bytes(const FusedCfg& f, bool bwd) {
   if (bwd) b += (size_t)f.threads * f.g * 4;
   return (b + 16 + 127) / 128 * 128;
 }
+// weight slices a CTA keeps in shared memory (floats): first FC 2C x D/cs, second FC 2C/cs x D, in either direction
+__host__ __device__ inline size_t l2_w1_floats(const FusedCfg& f) { return (f.wsm & 1) ? (size_t)2 * f.c * f.dq : 0; }
+__host__ __device__ inline size_t l2_w2_floats(const FusedCfg& f) { return (f.wsm & 2) ? (size_t)2 * f.cq * f.d : 0; }
 __host__ __device__ inline size_t l2_smem_bytes(const FusedCfg& f, bool bwd) {
-  return l2_small_bytes(f, bwd) + (size_t)f.keep_planes * f.hw * 4;
+  return l2_small_bytes(f, bwd) + (size_t)f.keep_planes * f.hw * 4 + (l2_w1_floats(f) + l2_w2_floats(f)) * 4;
 }
+__device__ __forceinline__ void cpa16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ L2Smem l2_carve(unsigned char* p, const FusedCfg& f) {
   L2Smem s;
   s.vec_a = reinterpret_cast<float*>(p); p += (size_t)f.g * 2 * f.c * 4;
@@ -756,6 +772,21 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   for (int i = tid; i < f.dq; i += T) s.bias_h[i] = __ldg(a.b_sq + rank * f.dq + i);
   for (int i = tid; i < 2 * f.cq; i += T)
     s.bias_g[i] = __ldg((i < f.cq ? a.b_v : a.b_s) + rank * f.cq + (i < f.cq ? i : i - f.cq));
+  // This CTA's rows of the FC weights (W_sq rows [rank*dq, +dq), W_v / W_s rows [rank*cq, +cq): contiguous blocks)
+  // start their way into shared memory now and land while pass 1 streams: the GEMVs of the chain then run without an
+  // L2 round trip, which under load costs ~3000 cycles each (profiles/r1_l2_resident_phase_trace.txt: fc1, fc2)
+  float* wsm1 = reinterpret_cast<float*>(smem_raw + l2_small_bytes(f, false) + (size_t)f.keep_planes * f.hw * 4);
+  float* wsm2 = wsm1 + l2_w1_floats(f);
+  if (f.wsm & 1) {
+    const float* src = a.w_sq + (size_t)rank * f.dq * 2 * f.c;
+    for (int i = tid * 4; i < f.dq * 2 * f.c; i += T * 4) cpa16(wsm1 + i, src + i);
+  }
+  if (f.wsm & 2) {
+    const int nw = f.cq * f.d;
+    const float* sv = a.w_v + (size_t)rank * nw;
+    const float* ss = a.w_s + (size_t)rank * nw;
+    for (int i = tid * 4; i < nw; i += T * 4) { cpa16(wsm2 + i, sv + i); cpa16(wsm2 + nw + i, ss + i); }
+  }
 
   constexpr int kPlanesPerPass = T / L;
   const int lane = tid % L, grp_in_pass = tid / L;
@@ -808,6 +839,7 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
     if (lane == 0) s.psum[p] = t;
   }
   GML_STAMP2(1);
+  if (f.wsm) cpa_wait_all();  // this thread's weight copies; the barrier below publishes them to the block
   cluster.sync();  // also: every CTA of the cluster is running before remote shared memory is touched
   GML_STAMP2(2);
   for (int p = tid; p < vplanes; p += T) {
@@ -816,42 +848,60 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
     const int k = mod * f.c + rank * f.cq + cl;
     const float mean = s.psum[p] / (float)f.hw;
     for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + k] = mean;
-    a.z[(size_t)(n0 + g) * 2 * f.c + k] = mean;
   }
+  // (z and h go out to global memory only after the chain: a global store issued here would have to be acknowledged
+  // before the releasing cluster barrier below completes -- a full L2 round trip on the critical path)
   cluster.sync();
   GML_STAMP2(3);
-  gemv_rows<T, GMAX>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
-                          2 * f.c, gcount, [&](int r, const float* acc) {
-                            const int dd = rank * f.dq + r;
-                            const float bias = s.bias_h[r];
-                            for (int g = 0; g < gcount; ++g) {
-                              const float hval = fmaxf(acc[g] + bias, 0.f);
-                              for (int dst = 0; dst < f.cs; ++dst)
-                                cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = hval;
-                              a.h[(size_t)(n0 + g) * f.d + dd] = hval;
-                            }
-                          });
+  auto epi_h = [&](int r, const float* acc) {
+    const int dd = rank * f.dq + r;
+    const float bias = s.bias_h[r];
+    for (int g = 0; g < gcount; ++g) {
+      const float hval = fmaxf(acc[g] + bias, 0.f);
+      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = hval;
+    }
+  };
+  if (f.wsm & 1)
+    gemv_rows<T, GMAX, true>([&](int r) { return wsm1 + (size_t)r * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a, 2 * f.c, gcount,
+                             epi_h);
+  else
+    gemv_rows<T, GMAX>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
+                       2 * f.c, gcount, epi_h);
   GML_STAMP2(4);
   cluster.sync();
   GML_STAMP2(5);
-  gemv_rows<T, GMAX>(
-      [&](int r) {
-        return r < f.cq ? a.w_v + (size_t)(rank * f.cq + r) * f.d : a.w_s + (size_t)(rank * f.cq + r - f.cq) * f.d;
-      },
-      2 * f.cq, f.d, s.vec_b, f.d, gcount, [&](int r, const float* acc) {
-        const int mod = r >= f.cq, cl = r - mod * f.cq;
-        const int ch = rank * f.cq + cl;
-        const float bias = s.bias_g[r];
-        float* gout = mod ? a.g_b : a.g_a;
-        for (int g = 0; g < gcount; ++g) {
-          const float gate = sigmoidf_ref(acc[g] + bias);
-          s.scale[(g * 2 + mod) * f.cq + cl] = gate * a.gate_scale;
-          gout[(size_t)(n0 + g) * f.c + ch] = gate;
-        }
-      });
+  auto epi_g = [&](int r, const float* acc) {
+    const int mod = r >= f.cq, cl = r - mod * f.cq;
+    const int ch = rank * f.cq + cl;
+    const float bias = s.bias_g[r];
+    float* gout = mod ? a.g_b : a.g_a;
+    for (int g = 0; g < gcount; ++g) {
+      const float gate = sigmoidf_ref(acc[g] + bias);
+      s.scale[(g * 2 + mod) * f.cq + cl] = gate * a.gate_scale;
+      gout[(size_t)(n0 + g) * f.c + ch] = gate;
+    }
+  };
+  if (f.wsm & 2)
+    gemv_rows<T, GMAX, true>([&](int r) { return wsm2 + (size_t)r * f.d; }, 2 * f.cq, f.d, s.vec_b, f.d, gcount, epi_g);
+  else
+    gemv_rows<T, GMAX>(
+        [&](int r) {
+          return r < f.cq ? a.w_v + (size_t)(rank * f.cq + r) * f.d : a.w_s + (size_t)(rank * f.cq + r - f.cq) * f.d;
+        },
+        2 * f.cq, f.d, s.vec_b, f.d, gcount, epi_g);
   GML_STAMP2(6);
   __syncthreads();
   GML_STAMP2(7);
+  // deferred exports of this CTA's share of z and h (fire and forget: nothing below waits for them)
+  for (int p = tid; p < vplanes; p += T) {
+    int g, mod, cl;
+    plane_coords(f, p, g, mod, cl);
+    a.z[(size_t)(n0 + g) * 2 * f.c + mod * f.c + rank * f.cq + cl] = s.psum[p] / (float)f.hw;
+  }
+  for (int i = tid; i < f.dq * gcount; i += T) {
+    const int g = i / f.dq, dd = rank * f.dq + (i - g * f.dq);
+    a.h[(size_t)(n0 + g) * f.d + dd] = s.vec_b[g * f.d + dd];
+  }
   // ---- pass 2: re-read (L2), gate, stream out ---------------------------------------------------
   for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
     int g, mod, cl;
@@ -912,6 +962,26 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const int g = tid / ncol_h, col = tid - g * ncol_h;
     h_pf = __ldg(a.h + (size_t)(n0 + g) * f.d + rank * f.dq + col);
   }
+  // weight slices into shared memory behind pass 1 (see l2_fwd_kernel): wsm1 = [W_v[:, cols] ; W_s[:, cols]] as
+  // [2C][dq] (cols = this CTA's dq hidden units), wsm2 = W_sq[:, this CTA's 2 cq squeeze columns] as [D][2 cq]
+  float* wsm1 = reinterpret_cast<float*>(smem_raw + l2_small_bytes(f, true) + (size_t)f.keep_planes * f.hw * 4);
+  float* wsm2 = wsm1 + l2_w1_floats(f);
+  if (f.wsm & 1) {
+    const int qpr = f.dq >> 2;  // 16-byte pieces per row
+    for (int i = tid; i < 2 * f.c * qpr; i += T) {
+      const int k = i / qpr, q = i - k * qpr;
+      const float* src = (k < f.c ? a.w_v + (size_t)k * f.d : a.w_s + (size_t)(k - f.c) * f.d) + rank * f.dq + 4 * q;
+      cpa16(wsm1 + (size_t)k * f.dq + 4 * q, src);
+    }
+  }
+  if (f.wsm & 2) {
+    const int qpr = ncol_z >> 2;
+    for (int i = tid; i < f.d * qpr; i += T) {
+      const int k = i / qpr, col = 4 * (i - k * qpr);
+      const int gcol = col < f.cq ? rank * f.cq + col : f.c + rank * f.cq + (col - f.cq);
+      cpa16(wsm2 + (size_t)k * ncol_z + col, a.w_sq + (size_t)k * 2 * f.c + gcol);
+    }
+  }
   if (f.prefetch > 0 && grp + f.prefetch < f.n_groups) {
     const int pn0 = (grp + f.prefetch) * f.g;
     const int pvplanes = min(f.g, f.n - pn0) * 2 * f.cq;
@@ -957,6 +1027,7 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const float t = group_sum<L>((a0 + a1) + (a2 + a3));
     if (lane == 0) s.psum[p] = t;
   }
+  if (f.wsm) cpa_wait_all();
   cluster.sync();
   if (tid < vplanes) {
     const int p = tid;
@@ -966,12 +1037,18 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const float de = s.psum[p] * a.gate_scale * gate_pf * (1.f - gate_pf);
     s.scale[p] = gate_pf * a.gate_scale;
     for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + mod * f.c + ch] = de;
-    (mod ? a.de_b : a.de_a)[(size_t)(n0 + g) * f.c + ch] = de;
   }
+  // (dE and dH are exported after the chain, see l2_fwd_kernel)
   for (int i = tid; i < T * GMAX; i += T) s.part[i] = 0.f;
   cluster.sync();
-  gemv_cols_partial<T, GMAX>(a.w_v, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
-  gemv_cols_partial<T, GMAX>(a.w_s, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount, s.part);
+  if (f.wsm & 1) {
+    gemv_cols_partial<T, GMAX, true>(wsm1, f.dq, 0, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
+    gemv_cols_partial<T, GMAX, true>(wsm1 + (size_t)f.c * f.dq, f.dq, 0, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount,
+                                     s.part);
+  } else {
+    gemv_cols_partial<T, GMAX>(a.w_v, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
+    gemv_cols_partial<T, GMAX>(a.w_s, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount, s.part);
+  }
   __syncthreads();
   {
     const int slices = T / ncol_h;
@@ -982,7 +1059,6 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
       const int dd = rank * f.dq + col;
       v = h_pf > 0.f ? v : 0.f;
       for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = v;
-      a.dh[(size_t)(n0 + g) * f.d + dd] = v;
     }
   }
   cluster.sync();
@@ -995,12 +1071,22 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     float acc[GMAX];
 #pragma unroll
     for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
+    if (f.wsm & 2) {
 #pragma unroll 16
-    for (int kk = ka; kk < kb; ++kk) {
-      const float wv = __ldg(a.w_sq + (size_t)kk * 2 * f.c + gcol);
+      for (int kk = ka; kk < kb; ++kk) {
+        const float wv = wsm2[(size_t)kk * ncol_z + col];
 #pragma unroll
-      for (int g = 0; g < GMAX; ++g)
-        if (g < gcount) acc[g] = fmaf(s.vec_b[g * f.d + kk], wv, acc[g]);
+        for (int g = 0; g < GMAX; ++g)
+          if (g < gcount) acc[g] = fmaf(s.vec_b[g * f.d + kk], wv, acc[g]);
+      }
+    } else {
+#pragma unroll 16
+      for (int kk = ka; kk < kb; ++kk) {
+        const float wv = __ldg(a.w_sq + (size_t)kk * 2 * f.c + gcol);
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g)
+          if (g < gcount) acc[g] = fmaf(s.vec_b[g * f.d + kk], wv, acc[g]);
+      }
     }
 #pragma unroll
     for (int g = 0; g < GMAX; ++g) s.part[((size_t)sl * GMAX + g) * ncol_z + col] = acc[g];
@@ -1014,6 +1100,16 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     }
   }
   __syncthreads();
+  if (tid < vplanes) {   // deferred exports: this CTA's share of dE and dH
+    int g, mod, cl;
+    plane_coords(f, tid, g, mod, cl);
+    const int ch = rank * f.cq + cl;
+    (mod ? a.de_b : a.de_a)[(size_t)(n0 + g) * f.c + ch] = s.vec_a[g * 2 * f.c + mod * f.c + ch];
+  }
+  if (tid < ncol_h * gcount) {
+    const int g = tid / ncol_h, dd = rank * f.dq + (tid - g * ncol_h);
+    a.dh[(size_t)(n0 + g) * f.d + dd] = s.vec_b[g * f.d + dd];
+  }
   // ---- pass 2: d_input = grad_out (L2 re-read) * scale + ds / HW ---------------------------------
   for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
     int g, mod, cl;
@@ -1044,7 +1140,7 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   // no trailing cluster barrier (see forward)
 }
 
-bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
+bool make_cfg_l2(int n, int c, int hw, int d, int cs, bool bwd, FusedCfg* out) {
   if (n <= 0 || c % (4 * cs) != 0 || d % (4 * cs) != 0 || hw % 4 != 0) return false;
   FusedCfg f;
   f.n = n; f.c = c; f.hw = hw; f.d = d; f.cs = cs; f.threads = 256;
@@ -1061,8 +1157,28 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
   f.trace = g_fused_trace;
   f.trace_first = (f.n_groups / 2) * cs;
   f.prefetch = ((size_t)hw * 4) % 16 == 0 ? g_fused_prefetch : 0;  // look-ahead distance in groups
-  f.keep_planes = (int)(((size_t)g_fused_stash_kb * 1024) / ((size_t)hw * 4));
+  // shared memory per CTA: [exchange buffers][stash][weight slices].  Weight slices (2 x 2CD/cs floats) are taken when
+  // they still leave >= 8 KB of stash at four CTAs per SM; a forced mask may cost occupancy instead.
+  f.wsm = 0; f.keep_planes = 0;
+  const size_t small = l2_small_bytes(f, bwd), plane = (size_t)hw * 4;
+  const size_t w1 = (size_t)2 * c * f.dq * 4, w2 = (size_t)2 * f.cq * d * 4;
+  const size_t lim4 = 46 * 1024;  // measured (profiles/r2_sweep.md): 44.3 KB per CTA runs at full speed, 49.4 KB does not
+  int mask = g_fused_wsmem;
+  if (mask < 0) mask = (small + w1 + w2 + 8 * 1024 <= lim4) ? 3 : 0;
+  const size_t wbytes = ((mask & 1) ? w1 : 0) + ((mask & 2) ? w2 : 0);
+  size_t stash = (size_t)g_fused_stash_kb * 1024;
+  if (wbytes) {
+    size_t lim = lim4;
+    if (small + wbytes > lim) lim = 75 * 1024;    // 3 CTAs per SM
+    if (small + wbytes > lim) lim = 113 * 1024;   // 2
+    if (small + wbytes > lim) lim = 227 * 1024;   // 1
+    if (small + wbytes > lim) return false;
+    if (stash > lim - small - wbytes) stash = lim - small - wbytes;
+  }
+  f.wsm = mask & 3;
+  f.keep_planes = (int)(stash / plane);
   if (f.keep_planes > f.pl) f.keep_planes = f.pl;
+  if (l2_smem_bytes(f, bwd) > 227 * 1024) return false;
   if ((long long)f.n_groups * cs > 0x7fffffffLL) return false;
   *out = f;
   return true;
@@ -1071,6 +1187,12 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, FusedCfg* out) {
 template <typename Args, typename K>
 int do_launch_l2(K kern, const Args& args, const FusedCfg& f, bool bwd, cudaStream_t st, int tag) {
   const size_t smem = l2_smem_bytes(f, bwd);
+  {
+    static const bool dbg = getenv("GML_DEBUG_CFG") != nullptr;
+    if (dbg)
+      fprintf(stderr, "[gml] l2 %s: cs=%d g=%d wsm=%d (tunable %d) keep=%d smem=%zu stash_kb=%d\n", bwd ? "bwd" : "fwd", f.cs,
+              f.g, f.wsm, g_fused_wsmem, f.keep_planes, smem, g_fused_stash_kb);
+  }
   if (smem > 48 * 1024) GML_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (f.cs > 8) GML_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -1133,10 +1255,17 @@ static bool pick_cfg(int n, int c, int hw, int d, FusedCfg* f, bool* l2, bool bw
   if (use_l2_kind()) {
     // measured on B200 (profiles/): the forward prefers 8-CTA clusters (smaller L2 footprint in flight),
     // the backward 4-CTA clusters (fewer, larger transposed GEMVs)
+    // ... unless 8-CTA clusters can keep both weight slices in shared memory and the batch is large: 128x28^2 backward
+    // at batch 1024 0.488 ms (cs 8, weights in shared memory) vs 0.515 (cs 4) vs 0.620 (cs 8, weights from L2); at batch
+    // 256 cs 4 is still ahead (0.159 vs 0.163)
+    if (bwd && !g_fused_cluster && n >= 512 && make_cfg_l2(n, c, hw, d, 8, bwd, f) && f->wsm == 3 && weights_ok(*f)) {
+      *l2 = true;
+      return true;
+    }
     const int first = g_fused_cluster ? g_fused_cluster : (bwd ? 4 : 8);
     const int second = g_fused_cluster ? 0 : (bwd ? 8 : 4);
-    if (make_cfg_l2(n, c, hw, d, first, f) && weights_ok(*f)) { *l2 = true; return true; }
-    if (second && make_cfg_l2(n, c, hw, d, second, f) && weights_ok(*f)) { *l2 = true; return true; }
+    if (make_cfg_l2(n, c, hw, d, first, bwd, f) && weights_ok(*f)) { *l2 = true; return true; }
+    if (second && make_cfg_l2(n, c, hw, d, second, bwd, f) && weights_ok(*f)) { *l2 = true; return true; }
     if (g_fused_kind == 2) return false;
   }
   *l2 = false;
@@ -1183,6 +1312,7 @@ int launch_fused_bwd(const FusedBwdArgs& args, cudaStream_t st) {
   if (!aligned16(args.go_a) || !aligned16(args.go_b) || !aligned16(args.a) || !aligned16(args.b) ||
       !aligned16(args.d_a) || !aligned16(args.d_b))
     return GML_E_UNSUPPORTED;
+  if (l2 && f.wsm && (!aligned16(args.w_sq) || !aligned16(args.w_v) || !aligned16(args.w_s))) f.wsm = 0;
   if (l2) return dispatch_l2_bwd(args, f, st);
   return f.threads == 512 ? dispatch_bwd<512>(args, f, st) : dispatch_bwd<256>(args, f, st);
 }

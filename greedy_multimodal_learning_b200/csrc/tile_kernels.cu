@@ -47,6 +47,7 @@ int g_tile_chunk_kb = 28;   // tunable "tile_chunk_kb": upper bound of a backwar
 int g_tile_chunk_kb_fwd = 56;  // tunable "tile_chunk_kb_fwd": the same for the forward (one buffer per slot).  The loader warp
                             // spends ~1000 cycles per item whatever its size, so fewer, larger items stream faster:
                             // forward 128x28^2 0.434 -> 0.379 ms, 256x14^2 0.236 -> 0.213 ms (profiles/r2_sweep.md)
+int g_tile_light_fwd = 0;    // tunable "tile_light_fwd": 1 = forward of blocks with < 1 MB of weights on the pipeline from tile_min_mb_light on
 int g_tile_min_mb_light = 190;  // tunable "tile_min_mb_light": the same threshold for the forward of blocks with < 1 MB of weights
 int g_tile_min_mb = 96;     // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality (forward: half of it)
 int g_tile_ksplit_tiles = 0;  // tunable "tile_ksplit_tiles": k-tiles per split-K item (0 = no split-K: the deep pipeline hides the
@@ -1431,9 +1432,9 @@ bool tile_preferred(int n, int c, int hw, int d, bool bwd) {
   const size_t u = (size_t)n * c * hw * 4;
   const size_t w_bytes = (size_t)16 * c * d;
   if (w_bytes >= (1u << 20)) return u >= ((size_t)g_tile_min_mb << 20) / (bwd ? 1 : 2);
-  // light-weight blocks (128 channels): the cluster kernels move 4u / 6u and win the backward; the forward of a large
-  // batch is faster through the pipeline's 56 KB items
-  return !bwd && u >= ((size_t)g_tile_min_mb_light << 20);
+  // light-weight blocks (128 channels): the cluster kernels move 4u / 6u and, with their weight slices in shared memory,
+  // win both directions (128x28^2 forward at batch 1024: 0.357 ms vs 0.381 ms through the pipeline's 56 KB items)
+  return !bwd && g_tile_light_fwd && u >= ((size_t)g_tile_min_mb_light << 20);
 }
 
 // K-major copies for the weight-gradient GEMMs: H^T, dH^T [D, ldT] and Z^T, dE^T [2C, ldT], ldT = N rounded up to 32

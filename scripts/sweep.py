@@ -89,6 +89,24 @@ VARIANTS = {
     "g_lag8_m64": (L.F_FORCE_TILE, {"tile_lag": 8, "tile_m": 64}),
     "g_lag16_m64": (L.F_FORCE_TILE, {"tile_lag": 16, "tile_m": 64}),
     "g_lag12_m64": (L.F_FORCE_TILE, {"tile_lag": 12, "tile_m": 64}),
+    "old_ws0": (0, {"tile_kind": 2, "fused_wsmem": 0}),
+    "old_ws1": (0, {"tile_kind": 2, "fused_wsmem": 1}),
+    "old_ws2": (0, {"tile_kind": 2, "fused_wsmem": 2}),
+    "old_ws3": (0, {"tile_kind": 2, "fused_wsmem": 3}),
+    "old_ws3_st0": (0, {"tile_kind": 2, "fused_wsmem": 3, "fused_stash_kb": 0}),
+    "old_ws3_st12": (0, {"tile_kind": 2, "fused_wsmem": 3, "fused_stash_kb": 12}),
+    "old_ws3_st8": (0, {"tile_kind": 2, "fused_wsmem": 3, "fused_stash_kb": 8}),
+    "old_ws3_st16": (0, {"tile_kind": 2, "fused_wsmem": 3, "fused_stash_kb": 16}),
+    "old_ws1_st12": (0, {"tile_kind": 2, "fused_wsmem": 1, "fused_stash_kb": 12}),
+    "old_ws2_st12": (0, {"tile_kind": 2, "fused_wsmem": 2, "fused_stash_kb": 12}),
+    "old_ws1_st0": (0, {"tile_kind": 2, "fused_wsmem": 1, "fused_stash_kb": 0}),
+    "old_ws2_st0": (0, {"tile_kind": 2, "fused_wsmem": 2, "fused_stash_kb": 0}),
+    "old_ws0_st12": (0, {"tile_kind": 2, "fused_wsmem": 0, "fused_stash_kb": 12}),
+    "old_cs8_ws0": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_wsmem": 0}),
+    "old_cs8_ws3_st12": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_wsmem": 3, "fused_stash_kb": 12}),
+    "old_cs8_ws3_st8": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_wsmem": 3, "fused_stash_kb": 8}),
+    "old_cs8_ws3_st0": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_wsmem": 3, "fused_stash_kb": 0}),
+    "light_tile": (0, {"tile_light_fwd": 1}),
     "w_nofold": (0, {"tile_wgrad": 0}),
     "w_g16": (0, {"tile_gemm_ctas": 16}),
     "w_g20": (0, {"tile_gemm_ctas": 20}),
@@ -258,6 +276,7 @@ def main():
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--variants", default=",".join(VARIANTS))
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
+    ap.add_argument("--profile", action="store_true", help="print the library's per-kernel-class times per variant")
     ap.add_argument("--shapes", default="", help="comma-separated channel counts to keep (default: all three blocks)")
     args = ap.parse_args()
     keep = [int(x) for x in args.shapes.split(",") if x]
@@ -290,7 +309,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, "tile_switch": 1, "tile_rpol": 0, "tile_max_slots": 0, "tile_split_copies": 1, "tile_draw": 4, "tile_chunk_kb_fwd": 56, "tile_min_mb_light": 190, "tile_wgrad": 1, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": 24, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, "tile_switch": 1, "tile_rpol": 0, "tile_max_slots": 0, "tile_split_copies": 1, "tile_draw": 4, "tile_chunk_kb_fwd": 56, "tile_min_mb_light": 190, "tile_wgrad": 1, "fused_wsmem": -1, "tile_light_fwd": 0, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 # workspace sizes depend on the tile tunables: re-query for this variant
                 b.ws_bytes = lib.gml_mmtm_bwd_workspace_bytes(b.dims)
@@ -317,6 +336,23 @@ def main():
                     ts = sorted(ts[2:])
                     med = ts[len(ts) // 2]
                     res[what] = {"ms": med, "gbs": units * u / (med * 1e-3) / 1e9, "min_ms": ts[0]}
+                if args.profile:
+                    import ctypes
+                    for what, fn in (("fwd", fwd), ("bwd", bwd)):
+                        lib.gml_profile_reset()
+                        lib.gml_profile_enable(1)
+                        for _ in range(4):
+                            flush.zero_()
+                            L.check(fn(flags), what)
+                        torch.cuda.synchronize()
+                        lib.gml_profile_enable(0)
+                        parts = []
+                        for tag in range(lib.gml_kernel_tag_count()):
+                            t_, c_ = ctypes.c_double(), ctypes.c_int64()
+                            lib.gml_profile_read(tag, ctypes.byref(t_), ctypes.byref(c_))
+                            if c_.value:
+                                parts.append("%s %.3f ms x%d" % (lib.gml_kernel_tag_name(tag).decode(), t_.value / 4, c_.value // 4))
+                        print("    %s %s: %s" % (name, what, "; ".join(parts)), flush=True)
                 tot = res["fwd"]["ms"] + res["bwd"]["ms"]
                 row = {"c": c, "h": h, "n": n, "variant": name, "fwd_ms": res["fwd"]["ms"], "bwd_ms": res["bwd"]["ms"],
                        "fwd_gbs": res["fwd"]["gbs"], "bwd_gbs": res["bwd"]["gbs"],
