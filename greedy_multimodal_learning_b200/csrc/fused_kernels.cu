@@ -47,6 +47,10 @@ int g_fused_stash_kb = 24; // L2-resident kernels: shared memory per CTA used to
 int g_fused_wsmem = -1;    // L2-resident kernels: FC weight slices prefetched into shared memory (cp.async, hidden behind pass 1);
                            // -1 auto (whatever fits at 4 CTAs per SM), else bit 0 = first FC, bit 1 = second FC
 int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch look-ahead distance in groups (0 = off)
+int g_fused_xchg = 1;      // L2-resident kernels: 1 = squeeze / hidden vectors travel between the CTAs of a cluster as st.async
+                           // stores that complete on the receiver's mbarrier (no cluster barrier, no MEMBAR in the chain),
+                           // 0 = plain DSMEM stores + cluster barriers
+long long* g_fused_occ_trace = nullptr;  // debug: per-CTA {smid, start ns, end ns, 0} of the L2-resident kernels (4 slots per CTA)
 long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
 namespace {
@@ -70,6 +74,8 @@ struct FusedCfg {
   int prefetch;      // L2-resident kernels: issue bulk L2 prefetches of the CTA's planes up front
   int trace_first;   // first CTA of the traced window (L2-resident kernels)
   int keep_planes;   // L2-resident kernels: the first keep_planes planes of a CTA are stashed in shared memory
+  int xchg;              // L2-resident kernels: st.async + mbarrier exchange (see g_fused_xchg)
+  long long* occ_trace;  // nullptr unless the residency trace is on
   int wsm;           // L2-resident kernels: bit 0 / bit 1 = weight slice of the first / second FC lives in shared memory
 };
 
@@ -630,6 +636,8 @@ bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out
   f.prefetch = 0;
   f.keep_planes = 0;
   f.wsm = 0;
+  f.occ_trace = nullptr;
+  f.xchg = 0;
   const size_t total = f.data_bytes + extras_bytes(f, true);
   if (total > (cs == 4 ? 232448u : 115000u)) return false;
   *out = f;
@@ -757,6 +765,38 @@ __device__ __forceinline__ L2Smem l2_carve(unsigned char* p, const FusedCfg& f) 
   return s;
 }
 
+// ---- cluster exchange without barriers: a value is stored into a peer's shared memory with st.async, which also
+// counts its bytes on an mbarrier in that peer; the peer waits for "all bytes of the vector have arrived"
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// the two exchange barriers live in the last 16 bytes of the "small" region (l2_small_bytes rounds up past them)
+__device__ __forceinline__ uint64_t* l2_xchg_bars(unsigned char* smem, const FusedCfg& f, bool bwd) {
+  return reinterpret_cast<uint64_t*>(smem + l2_small_bytes(f, bwd) - 16);
+}
+
+__device__ __forceinline__ void occ_stamp(const FusedCfg& f, int slot) {
+  if (f.occ_trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (slot == 1) {
+      unsigned sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      f.occ_trace[(size_t)blockIdx.x * 4 + 0] = sm;
+    }
+    f.occ_trace[(size_t)blockIdx.x * 4 + slot] = (long long)t;
+  }
+}
+
 template <int T, int L, int GMAX, int OCC>
 __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, const FusedCfg f) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -768,6 +808,20 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   // pass 2 -- shared memory used as extra register space, no synchronisation, no L2 re-read
   float4* stash = reinterpret_cast<float4*>(smem_raw + l2_small_bytes(f, false));
   const int tid = threadIdx.x;
+  occ_stamp(f, 1);
+  uint64_t* xbar = l2_xchg_bars(smem_raw, f, false);
+  if (f.xchg) {
+    const int gc = min(f.g, f.n - grp * f.g);
+    if (tid == 0) {
+      mbar_init(&xbar[0], 1);
+      mbar_init(&xbar[1], 1);
+      fence_mbar_init();
+      mbar_expect_tx(&xbar[0], (uint32_t)(gc * 2 * f.c * 4));   // the whole squeeze vector(s), from all CTAs
+      mbar_expect_tx(&xbar[1], (uint32_t)(gc * f.d * 4));       // the whole hidden vector(s)
+    }
+    __syncwarp();
+    cluster_arrive();  // matched by cluster_wait() before the first remote store: peers' barriers are initialised by then
+  }
   const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
   for (int i = tid; i < f.dq; i += T) s.bias_h[i] = __ldg(a.b_sq + rank * f.dq + i);
   for (int i = tid; i < 2 * f.cq; i += T)
@@ -840,25 +894,46 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   }
   GML_STAMP2(1);
   if (f.wsm) cpa_wait_all();  // this thread's weight copies; the barrier below publishes them to the block
-  cluster.sync();  // also: every CTA of the cluster is running before remote shared memory is touched
-  GML_STAMP2(2);
-  for (int p = tid; p < vplanes; p += T) {
-    int g, mod, cl;
-    plane_coords(f, p, g, mod, cl);
-    const int k = mod * f.c + rank * f.cq + cl;
-    const float mean = s.psum[p] / (float)f.hw;
-    for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + k] = mean;
+  if (f.xchg) {
+    __syncthreads();
+    cluster_wait();
+    GML_STAMP2(2);
+    const uint32_t va = smem_u32(s.vec_a), xb = smem_u32(&xbar[0]);
+    for (int p = tid; p < vplanes; p += T) {
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      const int k = mod * f.c + rank * f.cq + cl;
+      const float mean = s.psum[p] / (float)f.hw;
+      for (int dst = 0; dst < f.cs; ++dst)
+        st_async_f32(mapa_u32(va + (uint32_t)(g * 2 * f.c + k) * 4u, dst), mean, mapa_u32(xb, dst));
+    }
+    mbar_wait(&xbar[0], 0);
+  } else {
+    cluster.sync();  // also: every CTA of the cluster is running before remote shared memory is touched
+    GML_STAMP2(2);
+    for (int p = tid; p < vplanes; p += T) {
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      const int k = mod * f.c + rank * f.cq + cl;
+      const float mean = s.psum[p] / (float)f.hw;
+      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + k] = mean;
+    }
+    // (z and h go out to global memory only after the chain: a global store issued here would have to be acknowledged
+    // before the releasing cluster barrier below completes -- a full L2 round trip on the critical path)
+    cluster.sync();
   }
-  // (z and h go out to global memory only after the chain: a global store issued here would have to be acknowledged
-  // before the releasing cluster barrier below completes -- a full L2 round trip on the critical path)
-  cluster.sync();
   GML_STAMP2(3);
   auto epi_h = [&](int r, const float* acc) {
     const int dd = rank * f.dq + r;
     const float bias = s.bias_h[r];
     for (int g = 0; g < gcount; ++g) {
       const float hval = fmaxf(acc[g] + bias, 0.f);
-      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = hval;
+      if (f.xchg) {
+        const uint32_t vb = smem_u32(s.vec_b) + (uint32_t)(g * f.d + dd) * 4u, xb = smem_u32(&xbar[1]);
+        for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(vb, dst), hval, mapa_u32(xb, dst));
+      } else {
+        for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = hval;
+      }
     }
   };
   if (f.wsm & 1)
@@ -868,7 +943,8 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
     gemv_rows<T, GMAX>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
                        2 * f.c, gcount, epi_h);
   GML_STAMP2(4);
-  cluster.sync();
+  if (f.xchg) mbar_wait(&xbar[1], 0);
+  else cluster.sync();
   GML_STAMP2(5);
   auto epi_g = [&](int r, const float* acc) {
     const int mod = r >= f.cq, cl = r - mod * f.cq;
@@ -930,6 +1006,8 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   }
   GML_STAMP2(8);
   GML_STAMP2(9);
+  __syncthreads();  // (trace builds only matter: the end stamp is the CTA's, not warp 0's)
+  occ_stamp(f, 2);
   // no trailing cluster barrier: remote shared-memory writes only happen before the third barrier
 #undef GML_STAMP2
 }
@@ -943,6 +1021,21 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   const L2Smem s = l2_carve(smem_raw, f);
   float4* stash = reinterpret_cast<float4*>(smem_raw + l2_small_bytes(f, true));  // see l2_fwd_kernel
   const int tid = threadIdx.x;
+  occ_stamp(f, 1);
+  uint64_t* xbar = l2_xchg_bars(smem_raw, f, true);
+  if (f.xchg) {
+    const int gc = min(f.g, f.n - grp * f.g);
+    if (tid == 0) {
+      mbar_init(&xbar[0], 1);
+      mbar_init(&xbar[1], 1);
+      fence_mbar_init();
+      mbar_expect_tx(&xbar[0], (uint32_t)(gc * 2 * f.c * 4));   // dE of both modalities, from all CTAs
+      mbar_expect_tx(&xbar[1], (uint32_t)(gc * f.d * 4));       // dH
+    }
+    __syncwarp();
+    cluster_arrive();
+    for (int i = tid; i < T * GMAX; i += T) s.part[i] = 0.f;   // (published by the __syncthreads after pass 1)
+  }
   const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
   constexpr int kPlanesPerPass = T / L;
   const int lane = tid % L, grp_in_pass = tid / L;
@@ -951,6 +1044,10 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   const int n0 = grp * f.g;
   const int gcount = min(f.g, f.n - n0);
   const int vplanes = gcount * 2 * f.cq;
+  const int iter = 0;
+  const bool stamp_me = f.trace && threadIdx.x == 0 && blockIdx.x >= f.trace_first && blockIdx.x < f.trace_first + 8;
+#define GML_STAMP2(k) do { if (stamp_me) f.trace[((size_t)(blockIdx.x - f.trace_first) * 16 + iter) * 16 + (k)] = clock64(); } while (0)
+  GML_STAMP2(0);
 
   float gate_pf = 0.f, h_pf = 0.f;
   if (tid < vplanes) {
@@ -1027,20 +1124,40 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const float t = group_sum<L>((a0 + a1) + (a2 + a3));
     if (lane == 0) s.psum[p] = t;
   }
+  GML_STAMP2(1);
   if (f.wsm) cpa_wait_all();
-  cluster.sync();
-  if (tid < vplanes) {
-    const int p = tid;
-    int g, mod, cl;
-    plane_coords(f, p, g, mod, cl);
-    const int ch = rank * f.cq + cl;
-    const float de = s.psum[p] * a.gate_scale * gate_pf * (1.f - gate_pf);
-    s.scale[p] = gate_pf * a.gate_scale;
-    for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + mod * f.c + ch] = de;
+  if (f.xchg) {
+    __syncthreads();
+    cluster_wait();
+    GML_STAMP2(2);
+    if (tid < vplanes) {
+      const int p = tid;
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      const int ch = rank * f.cq + cl;
+      const float de = s.psum[p] * a.gate_scale * gate_pf * (1.f - gate_pf);
+      s.scale[p] = gate_pf * a.gate_scale;
+      const uint32_t va = smem_u32(s.vec_a) + (uint32_t)(g * 2 * f.c + mod * f.c + ch) * 4u, xb = smem_u32(&xbar[0]);
+      for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(va, dst), de, mapa_u32(xb, dst));
+    }
+    mbar_wait(&xbar[0], 0);
+  } else {
+    cluster.sync();
+    GML_STAMP2(2);
+    if (tid < vplanes) {
+      const int p = tid;
+      int g, mod, cl;
+      plane_coords(f, p, g, mod, cl);
+      const int ch = rank * f.cq + cl;
+      const float de = s.psum[p] * a.gate_scale * gate_pf * (1.f - gate_pf);
+      s.scale[p] = gate_pf * a.gate_scale;
+      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + mod * f.c + ch] = de;
+    }
+    // (dE and dH are exported after the chain, see l2_fwd_kernel)
+    for (int i = tid; i < T * GMAX; i += T) s.part[i] = 0.f;
+    cluster.sync();
   }
-  // (dE and dH are exported after the chain, see l2_fwd_kernel)
-  for (int i = tid; i < T * GMAX; i += T) s.part[i] = 0.f;
-  cluster.sync();
+  GML_STAMP2(3);
   if (f.wsm & 1) {
     gemv_cols_partial<T, GMAX, true>(wsm1, f.dq, 0, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
     gemv_cols_partial<T, GMAX, true>(wsm1 + (size_t)f.c * f.dq, f.dq, 0, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount,
@@ -1058,10 +1175,18 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
       for (int sl = 0; sl < slices; ++sl) v += s.part[((size_t)sl * GMAX + g) * ncol_h + col];
       const int dd = rank * f.dq + col;
       v = h_pf > 0.f ? v : 0.f;
-      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = v;
+      if (f.xchg) {
+        const uint32_t vb = smem_u32(s.vec_b) + (uint32_t)(g * f.d + dd) * 4u, xb = smem_u32(&xbar[1]);
+        for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(vb, dst), v, mapa_u32(xb, dst));
+      } else {
+        for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = v;
+      }
     }
   }
-  cluster.sync();
+  GML_STAMP2(4);
+  if (f.xchg) mbar_wait(&xbar[1], 0);
+  else cluster.sync();
+  GML_STAMP2(5);
   {
     const int slices = T / ncol_z;
     const int col = tid % ncol_z, sl = tid / ncol_z;
@@ -1099,7 +1224,9 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
       s.addv[(g * 2 + mod) * f.cq + cl] = v / (float)f.hw;
     }
   }
+  GML_STAMP2(6);
   __syncthreads();
+  GML_STAMP2(7);
   if (tid < vplanes) {   // deferred exports: this CTA's share of dE and dH
     int g, mod, cl;
     plane_coords(f, tid, g, mod, cl);
@@ -1137,7 +1264,12 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
       }
     }
   }
+  GML_STAMP2(8);
+  GML_STAMP2(9);
+  __syncthreads();
+  occ_stamp(f, 2);
   // no trailing cluster barrier (see forward)
+#undef GML_STAMP2
 }
 
 bool make_cfg_l2(int n, int c, int hw, int d, int cs, bool bwd, FusedCfg* out) {
@@ -1155,6 +1287,8 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, bool bwd, FusedCfg* out) {
   f.n_groups = (n + f.g - 1) / f.g;
   f.data_bytes = 0;
   f.trace = g_fused_trace;
+  f.occ_trace = g_fused_occ_trace;
+  f.xchg = g_fused_xchg;
   f.trace_first = (f.n_groups / 2) * cs;
   f.prefetch = ((size_t)hw * 4) % 16 == 0 ? g_fused_prefetch : 0;  // look-ahead distance in groups
   // shared memory per CTA: [exchange buffers][stash][weight slices].  Weight slices (2 x 2CD/cs floats) are taken when

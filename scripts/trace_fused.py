@@ -14,7 +14,8 @@ lib = L.load()
 dev = torch.device("cuda:0")
 NAMES = ["pass1", "sync", "scatter+csync", "fc1", "csync", "fc2", "sync", "pass2", "sync"]
 KIND = int(os.environ.get("TRACE_KIND", "1"))
-for (c, h, n) in ((128, 28, int(os.environ.get("TRACE_N", "256"))), (256, 14, int(os.environ.get("TRACE_N", "256")))):
+SHAPES = [(128, 28), (256, 14)] if not os.environ.get("TRACE_C") else [(int(os.environ["TRACE_C"]), {128: 28, 256: 14}[int(os.environ["TRACE_C"])])]
+for (c, h, n) in [(c_, h_, int(os.environ.get("TRACE_N", "256"))) for c_, h_ in SHAPES]:
     for cs, thr in (((4, 512), (8, 256)) if KIND == 1 else ((8, 0), (4, 0))):
         L.check(lib.gml_set_tunable(b"fused_kind", KIND))
         L.check(lib.gml_set_tunable(b"fused_cluster", cs))
