@@ -47,9 +47,6 @@ int g_fused_stash_kb = 24; // L2-resident kernels: shared memory per CTA used to
 int g_fused_wsmem = -1;    // L2-resident kernels: FC weight slices prefetched into shared memory (cp.async, hidden behind pass 1);
                            // -1 auto (whatever fits at 4 CTAs per SM), else bit 0 = first FC, bit 1 = second FC
 int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch look-ahead distance in groups (0 = off)
-int g_fused_xchg = 1;      // L2-resident kernels: 1 = squeeze / hidden vectors travel between the CTAs of a cluster as st.async
-                           // stores that complete on the receiver's mbarrier (no cluster barrier, no MEMBAR in the chain),
-                           // 0 = plain DSMEM stores + cluster barriers
 long long* g_fused_occ_trace = nullptr;  // debug: per-CTA {smid, start ns, end ns, 0} of the L2-resident kernels (4 slots per CTA)
 long long* g_fused_trace = nullptr;  // debug: per-phase clock64() stamps of the first CTAs (device buffer)
 
@@ -74,7 +71,6 @@ struct FusedCfg {
   int prefetch;      // L2-resident kernels: issue bulk L2 prefetches of the CTA's planes up front
   int trace_first;   // first CTA of the traced window (L2-resident kernels)
   int keep_planes;   // L2-resident kernels: the first keep_planes planes of a CTA are stashed in shared memory
-  int xchg;              // L2-resident kernels: st.async + mbarrier exchange (see g_fused_xchg)
   long long* occ_trace;  // nullptr unless the residency trace is on
   int wsm;           // L2-resident kernels: bit 0 / bit 1 = weight slice of the first / second FC lives in shared memory
 };
@@ -206,7 +202,7 @@ __device__ __forceinline__ void plane_drained(const FusedCfg& f, const Smem& s, 
 // y[row] = <W[row0 + row, 0:K], x[g, 0:K]>, K % 4 == 0.  Each warp owns kRowsPerBatch rows at a time
 // and issues all their weight loads before the first FMA (the weights come from L2: the cost is
 // latency, so several rows must be in flight); lane r then finishes row r.
-template <int T, int GMAX, int R, bool SM, typename RowPtr, typename Epi>
+template <int T, int GMAX, int R, typename RowPtr, typename Epi>
 __device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
                                             Epi epi) {
   constexpr int kWarps = T / 32;
@@ -218,14 +214,13 @@ __device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, con
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int g = 0; g < GMAX; ++g) acc[r][g] = 0.f;
-#pragma unroll 2
+#pragma unroll 1
     for (int i = lane; i < k4; i += 32) {
       float4 wv[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int row = min(base + r, nrows - 1);  // clamp: duplicates are discarded in the epilogue
-        wv[r] = SM ? *(reinterpret_cast<const float4*>(rowptr(row)) + i)
-                   : __ldg(reinterpret_cast<const float4*>(rowptr(row)) + i);
+        wv[r] = *(reinterpret_cast<const float4*>(rowptr(row)) + i);  // generic load: global or shared memory
       }
 #pragma unroll
       for (int g = 0; g < GMAX; ++g) {
@@ -249,20 +244,21 @@ __device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, con
   }
 }
 
-// SM: the rows live in shared memory (plain loads) instead of global memory (ld.global.nc)
-template <int T, int GMAX, bool SM = false, typename RowPtr, typename Epi>
+// The rows may live in global or in shared memory (generic loads): one copy of the code serves both, which matters here --
+// with a separate instantiation per address space and per row batch the forward kernel was 14k instructions and its
+// once-per-CTA FC phases ran out of the instruction cache.
+template <int T, int GMAX, typename RowPtr, typename Epi>
 __device__ __forceinline__ void gemv_rows(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
                                           Epi epi) {
   // few rows: spread them over more warps (one L2 round trip either way)
-  if (nrows <= (T / 32)) gemv_rows_r<T, GMAX, 1, SM>(rowptr, nrows, k, x, ldx, gcount, epi);
-  else if (nrows <= 2 * (T / 32)) gemv_rows_r<T, GMAX, 2, SM>(rowptr, nrows, k, x, ldx, gcount, epi);
-  else gemv_rows_r<T, GMAX, kRowsPerBatch, SM>(rowptr, nrows, k, x, ldx, gcount, epi);
+  if (nrows <= 2 * (T / 32)) gemv_rows_r<T, GMAX, 2>(rowptr, nrows, k, x, ldx, gcount, epi);
+  else gemv_rows_r<T, GMAX, kRowsPerBatch>(rowptr, nrows, k, x, ldx, gcount, epi);
 }
 
 // y[col] = sum_k x[g, k] * W[k, col0 + col] (transposed GEMV): thread = (k-slice, col), coalesced in
 // col.  Partials are ADDED into s_part[slice][g][col]; the caller reduces the slices in a fixed order.
 template <int T, int GMAX, bool SM = false>
-__device__ __forceinline__ void gemv_cols_partial(const float* __restrict__ w, int ldw, int col0, int ncols, int k0,
+__device__ __forceinline__ void gemv_cols_partial(const float* w, int ldw, int col0, int ncols, int k0,
                                                   int k1, const float* x, int ldx, int gcount, float* s_part) {
   const int slices = T / ncols;
   const int col = threadIdx.x % ncols, sl = threadIdx.x / ncols;
@@ -274,6 +270,7 @@ __device__ __forceinline__ void gemv_cols_partial(const float* __restrict__ w, i
   const float* wp = w + col0 + col;
 #pragma unroll 16
   for (int kk = ka; kk < kb; ++kk) {
+    // (the strided global reads want the non-coherent path: generic loads made this GEMV ~2x slower)
     const float wv = SM ? wp[(size_t)kk * ldw] : __ldg(wp + (size_t)kk * ldw);
 #pragma unroll
     for (int g = 0; g < GMAX; ++g)
@@ -637,7 +634,6 @@ bool make_cfg_cs(int n, int c, int hw, int d, int cs, int threads, FusedCfg* out
   f.keep_planes = 0;
   f.wsm = 0;
   f.occ_trace = nullptr;
-  f.xchg = 0;
   const size_t total = f.data_bytes + extras_bytes(f, true);
   if (total > (cs == 4 ? 232448u : 115000u)) return false;
   *out = f;
@@ -810,7 +806,7 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   const int tid = threadIdx.x;
   occ_stamp(f, 1);
   uint64_t* xbar = l2_xchg_bars(smem_raw, f, false);
-  if (f.xchg) {
+  {
     const int gc = min(f.g, f.n - grp * f.g);
     if (tid == 0) {
       mbar_init(&xbar[0], 1);
@@ -854,18 +850,6 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
 #define GML_STAMP2(k) do { if (stamp_me) f.trace[((size_t)(blockIdx.x - f.trace_first) * 16 + iter) * 16 + (k)] = clock64(); } while (0)
   GML_STAMP2(0);
 
-  // ---- look-ahead: while this cluster is busy, the planes of the cluster that will run `prefetch`
-  // groups later are pulled HBM -> L2 by the bulk-prefetch engine (no registers, no shared memory)
-  if (f.prefetch > 0 && grp + f.prefetch < f.n_groups) {
-    const int pn0 = (grp + f.prefetch) * f.g;
-    const int pvplanes = min(f.g, f.n - pn0) * 2 * f.cq;
-    for (int p = tid; p < pvplanes; p += T) {
-      int g, mod, cl;
-      plane_coords(f, p, g, mod, cl);
-      bulk_prefetch_l2((mod ? a.b : a.a) + ((size_t)(pn0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw,
-                       (uint32_t)f.hw * 4u, pol_keep);
-    }
-  }
   // ---- pass 1: plane sums from HBM, lines asked to stay in L2 --------------------------------
   for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
     int g, mod, cl;
@@ -894,10 +878,13 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   }
   GML_STAMP2(1);
   if (f.wsm) cpa_wait_all();  // this thread's weight copies; the barrier below publishes them to the block
-  if (f.xchg) {
-    __syncthreads();
-    cluster_wait();
-    GML_STAMP2(2);
+  // The squeeze vector travels to every CTA of the cluster as st.async stores counted on the receiver's mbarrier: no
+  // cluster barrier and no MEMBAR on the chain (a cluster.sync() here cost ~2000 cycles, profiles/r2_cluster_kernels.md).
+  // z and h go out to global memory only after the chain.
+  __syncthreads();
+  cluster_wait();
+  GML_STAMP2(2);
+  {
     const uint32_t va = smem_u32(s.vec_a), xb = smem_u32(&xbar[0]);
     for (int p = tid; p < vplanes; p += T) {
       int g, mod, cl;
@@ -907,64 +894,44 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
       for (int dst = 0; dst < f.cs; ++dst)
         st_async_f32(mapa_u32(va + (uint32_t)(g * 2 * f.c + k) * 4u, dst), mean, mapa_u32(xb, dst));
     }
-    mbar_wait(&xbar[0], 0);
-  } else {
-    cluster.sync();  // also: every CTA of the cluster is running before remote shared memory is touched
-    GML_STAMP2(2);
-    for (int p = tid; p < vplanes; p += T) {
-      int g, mod, cl;
-      plane_coords(f, p, g, mod, cl);
-      const int k = mod * f.c + rank * f.cq + cl;
-      const float mean = s.psum[p] / (float)f.hw;
-      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + k] = mean;
-    }
-    // (z and h go out to global memory only after the chain: a global store issued here would have to be acknowledged
-    // before the releasing cluster barrier below completes -- a full L2 round trip on the critical path)
-    cluster.sync();
   }
+  mbar_wait(&xbar[0], 0);
   GML_STAMP2(3);
-  auto epi_h = [&](int r, const float* acc) {
-    const int dd = rank * f.dq + r;
-    const float bias = s.bias_h[r];
-    for (int g = 0; g < gcount; ++g) {
-      const float hval = fmaxf(acc[g] + bias, 0.f);
-      if (f.xchg) {
-        const uint32_t vb = smem_u32(s.vec_b) + (uint32_t)(g * f.d + dd) * 4u, xb = smem_u32(&xbar[1]);
-        for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(vb, dst), hval, mapa_u32(xb, dst));
-      } else {
-        for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = hval;
-      }
-    }
-  };
-  if (f.wsm & 1)
-    gemv_rows<T, GMAX, true>([&](int r) { return wsm1 + (size_t)r * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a, 2 * f.c, gcount,
-                             epi_h);
-  else
-    gemv_rows<T, GMAX>([&](int r) { return a.w_sq + (size_t)(rank * f.dq + r) * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a,
-                       2 * f.c, gcount, epi_h);
+  {
+    // FC1 rows of this CTA: shared-memory copy or global memory (row pointer = base + r * 2C either way)
+    const float* w1 = (f.wsm & 1) ? wsm1 : a.w_sq + (size_t)rank * f.dq * 2 * f.c;
+    const uint32_t vb0 = smem_u32(s.vec_b), xb = smem_u32(&xbar[1]);
+    gemv_rows<T, GMAX>([&](int r) { return w1 + (size_t)r * 2 * f.c; }, f.dq, 2 * f.c, s.vec_a, 2 * f.c, gcount,
+                       [&](int r, const float* acc) {
+                         const int dd = rank * f.dq + r;
+                         const float bias = s.bias_h[r];
+                         for (int g = 0; g < gcount; ++g) {
+                           const float hval = fmaxf(acc[g] + bias, 0.f);
+                           const uint32_t vb = vb0 + (uint32_t)(g * f.d + dd) * 4u;
+                           for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(vb, dst), hval, mapa_u32(xb, dst));
+                         }
+                       });
+  }
   GML_STAMP2(4);
-  if (f.xchg) mbar_wait(&xbar[1], 0);
-  else cluster.sync();
+  mbar_wait(&xbar[1], 0);
   GML_STAMP2(5);
-  auto epi_g = [&](int r, const float* acc) {
-    const int mod = r >= f.cq, cl = r - mod * f.cq;
-    const int ch = rank * f.cq + cl;
-    const float bias = s.bias_g[r];
-    float* gout = mod ? a.g_b : a.g_a;
-    for (int g = 0; g < gcount; ++g) {
-      const float gate = sigmoidf_ref(acc[g] + bias);
-      s.scale[(g * 2 + mod) * f.cq + cl] = gate * a.gate_scale;
-      gout[(size_t)(n0 + g) * f.c + ch] = gate;
-    }
-  };
-  if (f.wsm & 2)
-    gemv_rows<T, GMAX, true>([&](int r) { return wsm2 + (size_t)r * f.d; }, 2 * f.cq, f.d, s.vec_b, f.d, gcount, epi_g);
-  else
-    gemv_rows<T, GMAX>(
-        [&](int r) {
-          return r < f.cq ? a.w_v + (size_t)(rank * f.cq + r) * f.d : a.w_s + (size_t)(rank * f.cq + r - f.cq) * f.d;
-        },
-        2 * f.cq, f.d, s.vec_b, f.d, gcount, epi_g);
+  {
+    // FC2 rows: [W_v rows ; W_s rows] of this CTA's channels, contiguous in the shared-memory copy
+    const float* wv = (f.wsm & 2) ? wsm2 : a.w_v + (size_t)rank * f.cq * f.d;
+    const float* ws = (f.wsm & 2) ? wsm2 + (size_t)f.cq * f.d : a.w_s + (size_t)rank * f.cq * f.d;
+    gemv_rows<T, GMAX>([&](int r) { return r < f.cq ? wv + (size_t)r * f.d : ws + (size_t)(r - f.cq) * f.d; }, 2 * f.cq,
+                       f.d, s.vec_b, f.d, gcount, [&](int r, const float* acc) {
+                         const int mod = r >= f.cq, cl = r - mod * f.cq;
+                         const int ch = rank * f.cq + cl;
+                         const float bias = s.bias_g[r];
+                         float* gout = mod ? a.g_b : a.g_a;
+                         for (int g = 0; g < gcount; ++g) {
+                           const float gate = sigmoidf_ref(acc[g] + bias);
+                           s.scale[(g * 2 + mod) * f.cq + cl] = gate * a.gate_scale;
+                           gout[(size_t)(n0 + g) * f.c + ch] = gate;
+                         }
+                       });
+  }
   GML_STAMP2(6);
   __syncthreads();
   GML_STAMP2(7);
@@ -1023,7 +990,7 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   const int tid = threadIdx.x;
   occ_stamp(f, 1);
   uint64_t* xbar = l2_xchg_bars(smem_raw, f, true);
-  if (f.xchg) {
+  {
     const int gc = min(f.g, f.n - grp * f.g);
     if (tid == 0) {
       mbar_init(&xbar[0], 1);
@@ -1079,17 +1046,6 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
       cpa16(wsm2 + (size_t)k * ncol_z + col, a.w_sq + (size_t)k * 2 * f.c + gcol);
     }
   }
-  if (f.prefetch > 0 && grp + f.prefetch < f.n_groups) {
-    const int pn0 = (grp + f.prefetch) * f.g;
-    const int pvplanes = min(f.g, f.n - pn0) * 2 * f.cq;
-    for (int p = tid; p < pvplanes; p += T) {
-      int g, mod, cl;
-      plane_coords(f, p, g, mod, cl);
-      const size_t off = ((size_t)(pn0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
-      bulk_prefetch_l2((mod ? a.go_b : a.go_a) + off, (uint32_t)f.hw * 4u, pol_keep);
-      bulk_prefetch_l2((mod ? a.b : a.a) + off, (uint32_t)f.hw * 4u, pol_drop);
-    }
-  }
   // ---- pass 1: <grad_out (kept in L2), input (streamed once)> per plane --------------------------
   for (int p = grp_in_pass; p < vplanes; p += kPlanesPerPass) {
     int g, mod, cl;
@@ -1126,45 +1082,33 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   }
   GML_STAMP2(1);
   if (f.wsm) cpa_wait_all();
-  if (f.xchg) {
-    __syncthreads();
-    cluster_wait();
-    GML_STAMP2(2);
-    if (tid < vplanes) {
-      const int p = tid;
-      int g, mod, cl;
-      plane_coords(f, p, g, mod, cl);
-      const int ch = rank * f.cq + cl;
-      const float de = s.psum[p] * a.gate_scale * gate_pf * (1.f - gate_pf);
-      s.scale[p] = gate_pf * a.gate_scale;
-      const uint32_t va = smem_u32(s.vec_a) + (uint32_t)(g * 2 * f.c + mod * f.c + ch) * 4u, xb = smem_u32(&xbar[0]);
-      for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(va, dst), de, mapa_u32(xb, dst));
-    }
-    mbar_wait(&xbar[0], 0);
-  } else {
-    cluster.sync();
-    GML_STAMP2(2);
-    if (tid < vplanes) {
-      const int p = tid;
-      int g, mod, cl;
-      plane_coords(f, p, g, mod, cl);
-      const int ch = rank * f.cq + cl;
-      const float de = s.psum[p] * a.gate_scale * gate_pf * (1.f - gate_pf);
-      s.scale[p] = gate_pf * a.gate_scale;
-      for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_a, dst)[g * 2 * f.c + mod * f.c + ch] = de;
-    }
-    // (dE and dH are exported after the chain, see l2_fwd_kernel)
-    for (int i = tid; i < T * GMAX; i += T) s.part[i] = 0.f;
-    cluster.sync();
+  // dE of this CTA's channels -> every CTA of the cluster (st.async + mbarrier, see l2_fwd_kernel); dE and dH are
+  // exported to global memory after the chain
+  __syncthreads();
+  cluster_wait();
+  GML_STAMP2(2);
+  if (tid < vplanes) {
+    const int p = tid;
+    int g, mod, cl;
+    plane_coords(f, p, g, mod, cl);
+    const int ch = rank * f.cq + cl;
+    const float de = s.psum[p] * a.gate_scale * gate_pf * (1.f - gate_pf);
+    s.scale[p] = gate_pf * a.gate_scale;
+    const uint32_t va = smem_u32(s.vec_a) + (uint32_t)(g * 2 * f.c + mod * f.c + ch) * 4u, xb = smem_u32(&xbar[0]);
+    for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(va, dst), de, mapa_u32(xb, dst));
   }
+  mbar_wait(&xbar[0], 0);
   GML_STAMP2(3);
-  if (f.wsm & 1) {
-    gemv_cols_partial<T, GMAX, true>(wsm1, f.dq, 0, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
-    gemv_cols_partial<T, GMAX, true>(wsm1 + (size_t)f.c * f.dq, f.dq, 0, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount,
-                                     s.part);
-  } else {
-    gemv_cols_partial<T, GMAX>(a.w_v, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
-    gemv_cols_partial<T, GMAX>(a.w_s, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount, s.part);
+  {
+    // [W_v[:, cols] ; W_s[:, cols]]: shared-memory copy ([2C][dq]) or global memory ([C][D] each, column offset rank*dq)
+    if (f.wsm & 1) {
+      gemv_cols_partial<T, GMAX, true>(wsm1, f.dq, 0, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
+      gemv_cols_partial<T, GMAX, true>(wsm1 + (size_t)f.c * f.dq, f.dq, 0, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c,
+                                       gcount, s.part);
+    } else {
+      gemv_cols_partial<T, GMAX>(a.w_v, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a, 2 * f.c, gcount, s.part);
+      gemv_cols_partial<T, GMAX>(a.w_s, f.d, rank * f.dq, ncol_h, 0, f.c, s.vec_a + f.c, 2 * f.c, gcount, s.part);
+    }
   }
   __syncthreads();
   {
@@ -1175,17 +1119,12 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
       for (int sl = 0; sl < slices; ++sl) v += s.part[((size_t)sl * GMAX + g) * ncol_h + col];
       const int dd = rank * f.dq + col;
       v = h_pf > 0.f ? v : 0.f;
-      if (f.xchg) {
-        const uint32_t vb = smem_u32(s.vec_b) + (uint32_t)(g * f.d + dd) * 4u, xb = smem_u32(&xbar[1]);
-        for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(vb, dst), v, mapa_u32(xb, dst));
-      } else {
-        for (int dst = 0; dst < f.cs; ++dst) cluster.map_shared_rank(s.vec_b, dst)[g * f.d + dd] = v;
-      }
+      const uint32_t vb = smem_u32(s.vec_b) + (uint32_t)(g * f.d + dd) * 4u, xb = smem_u32(&xbar[1]);
+      for (int dst = 0; dst < f.cs; ++dst) st_async_f32(mapa_u32(vb, dst), v, mapa_u32(xb, dst));
     }
   }
   GML_STAMP2(4);
-  if (f.xchg) mbar_wait(&xbar[1], 0);
-  else cluster.sync();
+  mbar_wait(&xbar[1], 0);
   GML_STAMP2(5);
   {
     const int slices = T / ncol_z;
@@ -1288,7 +1227,6 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, bool bwd, FusedCfg* out) {
   f.data_bytes = 0;
   f.trace = g_fused_trace;
   f.occ_trace = g_fused_occ_trace;
-  f.xchg = g_fused_xchg;
   f.trace_first = (f.n_groups / 2) * cs;
   f.prefetch = ((size_t)hw * 4) % 16 == 0 ? g_fused_prefetch : 0;  // look-ahead distance in groups
   // shared memory per CTA: [exchange buffers][stash][weight slices].  Weight slices (2 x 2CD/cs floats) are taken when
@@ -1391,8 +1329,10 @@ static bool pick_cfg(int n, int c, int hw, int d, FusedCfg* f, bool* l2, bool bw
     // the backward 4-CTA clusters (fewer, larger transposed GEMVs)
     // ... unless 8-CTA clusters can keep both weight slices in shared memory and the batch is large: 128x28^2 backward
     // at batch 1024 0.488 ms (cs 8, weights in shared memory) vs 0.515 (cs 4) vs 0.620 (cs 8, weights from L2); at batch
-    // 256 cs 4 is still ahead (0.159 vs 0.163)
-    if (bwd && !g_fused_cluster && n >= 512 && make_cfg_l2(n, c, hw, d, 8, bwd, f) && f->wsm == 3 && weights_ok(*f)) {
+    // 128-256 cs 4 is still ahead (0.091 vs 0.095 ms at 128), at batch 32 the 8-CTA clusters win again by sheer CTA count
+    // (0.042 vs 0.050 ms)
+    if (bwd && !g_fused_cluster && (n >= 512 || n <= 64) && make_cfg_l2(n, c, hw, d, 8, bwd, f) && f->wsm == 3 &&
+        weights_ok(*f)) {
       *l2 = true;
       return true;
     }
