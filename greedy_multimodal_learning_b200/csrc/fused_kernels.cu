@@ -1329,10 +1329,8 @@ static bool pick_cfg(int n, int c, int hw, int d, FusedCfg* f, bool* l2, bool bw
     // the backward 4-CTA clusters (fewer, larger transposed GEMVs)
     // ... unless 8-CTA clusters can keep both weight slices in shared memory and the batch is large: 128x28^2 backward
     // at batch 1024 0.488 ms (cs 8, weights in shared memory) vs 0.515 (cs 4) vs 0.620 (cs 8, weights from L2); at batch
-    // 128-256 cs 4 is still ahead (0.091 vs 0.095 ms at 128), at batch 32 the 8-CTA clusters win again by sheer CTA count
-    // (0.042 vs 0.050 ms)
-    if (bwd && !g_fused_cluster && (n >= 512 || n <= 64) && make_cfg_l2(n, c, hw, d, 8, bwd, f) && f->wsm == 3 &&
-        weights_ok(*f)) {
+    // 128-256 cs 4 is still ahead (0.091 vs 0.095 ms at 128)
+    if (bwd && !g_fused_cluster && n >= 512 && make_cfg_l2(n, c, hw, d, 8, bwd, f) && f->wsm == 3 && weights_ok(*f)) {
       *l2 = true;
       return true;
     }
