@@ -201,7 +201,7 @@ __device__ __forceinline__ void plane_drained(const FusedCfg& f, const Smem& s, 
 
 // y[row] = <W[row0 + row, 0:K], x[g, 0:K]>, K % 4 == 0.  Each warp owns kRowsPerBatch rows at a time
 // and issues all their weight loads before the first FMA (the weights come from L2: the cost is
-// latency, so several rows must be in flight); lane r then finishes row r.
+// latency, so several rows must be in flight); lane r then finishes row r (see the end of the loop).
 template <int T, int GMAX, int R, typename RowPtr, typename Epi>
 __device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, const float* x, int ldx, int gcount,
                                             Epi epi) {
@@ -238,9 +238,17 @@ __device__ __forceinline__ void gemv_rows_r(RowPtr rowptr, int nrows, int k, con
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int g = 0; g < GMAX; ++g) acc[r][g] = warp_sum(acc[r][g]);
+    // every lane holds every sum (xor butterfly): lane r finishes row base + r, all R of them at once -- one copy of the
+    // epilogue, executed once per batch (R sequential single-lane epilogues, each a sigmoid or eight remote stores,
+    // were the longest part of the FC phases)
+    float mine[GMAX];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (lane == r && base + r < nrows) epi(base + r, acc[r]);
+    for (int g = 0; g < GMAX; ++g) {
+      mine[g] = acc[0][g];
+#pragma unroll
+      for (int r = 1; r < R; ++r) mine[g] = lane == r ? acc[r][g] : mine[g];
+    }
+    if (lane < R && base + lane < nrows) epi(base + lane, mine);
   }
 }
 

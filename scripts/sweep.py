@@ -107,6 +107,10 @@ VARIANTS = {
     "old_cs8_ws3_st8": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_wsmem": 3, "fused_stash_kb": 8}),
     "old_cs8_ws3_st0": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_wsmem": 3, "fused_stash_kb": 0}),
     "light_tile": (0, {"tile_light_fwd": 1}),
+    "c16_ws3": (0, {"tile_kind": 2, "fused_cluster": 16, "fused_wsmem": 3, "fused_stash_kb": 0}),
+    "c16_ws3_st12": (0, {"tile_kind": 2, "fused_cluster": 16, "fused_wsmem": 3, "fused_stash_kb": 12}),
+    "c16_ws0": (0, {"tile_kind": 2, "fused_cluster": 16, "fused_wsmem": 0}),
+    "c16_ws3_g1": (0, {"tile_kind": 2, "fused_cluster": 16, "fused_wsmem": 3, "fused_stash_kb": 0, "fused_group_kb": 1}),
     "p_st0": (0, {"fused_stash_kb": 0}),
     "p_st16": (0, {"fused_stash_kb": 16}),
     "p_occ5": (0, {"fused_occ": 5}),
