@@ -789,6 +789,10 @@ __device__ __forceinline__ uint64_t* l2_xchg_bars(unsigned char* smem, const Fus
 }
 
 __device__ __forceinline__ void occ_stamp(const FusedCfg& f, int slot) {
+#ifndef GML_L2_TRACE
+  (void)f; (void)slot;   // phase / residency tracing of the cluster kernels is compiled in with -DGML_L2_TRACE only
+  return;
+#endif
   if (f.occ_trace && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -855,7 +859,11 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   // phase stamps: trace the CTAs of the LAST-launched clusters' neighbours too -> use a mid-grid window
   const int iter = 0;
   const bool stamp_me = f.trace && threadIdx.x == 0 && blockIdx.x >= f.trace_first && blockIdx.x < f.trace_first + 8;
+#ifdef GML_L2_TRACE
 #define GML_STAMP2(k) do { if (stamp_me) f.trace[((size_t)(blockIdx.x - f.trace_first) * 16 + iter) * 16 + (k)] = clock64(); } while (0)
+#else
+#define GML_STAMP2(k) do { (void)stamp_me; (void)iter; } while (0)
+#endif
   GML_STAMP2(0);
 
   // ---- pass 1: plane sums from HBM, lines asked to stay in L2 --------------------------------
@@ -981,8 +989,10 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
   }
   GML_STAMP2(8);
   GML_STAMP2(9);
-  __syncthreads();  // (trace builds only matter: the end stamp is the CTA's, not warp 0's)
+#ifdef GML_L2_TRACE
+  __syncthreads();  // the end stamp is the CTA's, not warp 0's
   occ_stamp(f, 2);
+#endif
   // no trailing cluster barrier: remote shared-memory writes only happen before the third barrier
 #undef GML_STAMP2
 }
@@ -1021,7 +1031,11 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   const int vplanes = gcount * 2 * f.cq;
   const int iter = 0;
   const bool stamp_me = f.trace && threadIdx.x == 0 && blockIdx.x >= f.trace_first && blockIdx.x < f.trace_first + 8;
+#ifdef GML_L2_TRACE
 #define GML_STAMP2(k) do { if (stamp_me) f.trace[((size_t)(blockIdx.x - f.trace_first) * 16 + iter) * 16 + (k)] = clock64(); } while (0)
+#else
+#define GML_STAMP2(k) do { (void)stamp_me; (void)iter; } while (0)
+#endif
   GML_STAMP2(0);
 
   float gate_pf = 0.f, h_pf = 0.f;
@@ -1213,8 +1227,10 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   }
   GML_STAMP2(8);
   GML_STAMP2(9);
+#ifdef GML_L2_TRACE
   __syncthreads();
   occ_stamp(f, 2);
+#endif
   // no trailing cluster barrier (see forward)
 #undef GML_STAMP2
 }

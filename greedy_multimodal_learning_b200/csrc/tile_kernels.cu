@@ -49,7 +49,7 @@ int g_tile_chunk_kb_fwd = 56;  // tunable "tile_chunk_kb_fwd": the same for the 
                             // forward 128x28^2 0.434 -> 0.379 ms, 256x14^2 0.236 -> 0.213 ms (profiles/r2_sweep.md)
 int g_tile_light_fwd = 0;    // tunable "tile_light_fwd": 1 = forward of blocks with < 1 MB of weights on the pipeline from tile_min_mb_light on
 int g_tile_min_mb_light = 190;  // tunable "tile_min_mb_light": the same threshold for the forward of blocks with < 1 MB of weights
-int g_tile_min_mb = 96;     // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality (forward: two thirds of it)
+int g_tile_min_mb = 96;     // tunable "tile_min_mb": automatic mode takes the tile path from this many MB per modality (forward: x0.5 for >= 2 MB of FC weights, x1.5 below)
 int g_tile_ksplit_tiles = 0;  // tunable "tile_ksplit_tiles": k-tiles per split-K item (0 = no split-K: the deep pipeline hides the
                             // chain latency, and partial planes + folds cost more GEMM-CTA time than they save)
 int g_tile_switch = 1;      // tunable "tile_switch": GEMM CTAs join the stream role once the GEMM tickets are exhausted
@@ -1431,8 +1431,12 @@ bool tile_preferred(int n, int c, int hw, int d, bool bwd) {
   if (g_tile_kind == 1) return true;
   const size_t u = (size_t)n * c * hw * 4;
   const size_t w_bytes = (size_t)16 * c * d;
-  // (forward from 2/3 of the threshold: 256x14^2 at batch 256, 51 MB, is still faster on the cluster kernel, 0.087 vs 0.094 ms)
-  if (w_bytes >= (1u << 20)) return u >= (bwd ? (size_t)g_tile_min_mb << 20 : ((size_t)g_tile_min_mb << 20) * 2 / 3);
+  // Forward: 512x7^2 (4 MB of FC weights) from half the threshold (batch 512: 0.123 vs 0.126 ms), 256x14^2 (1 MB) only
+  // from 1.5x of it -- its cluster kernel still wins at batch 512 (0.126 vs 0.133 ms) and loses at 1024 (0.290 vs 0.205)
+  if (w_bytes >= (1u << 20)) {
+    const size_t base = (size_t)g_tile_min_mb << 20;
+    return u >= (bwd ? base : (w_bytes >= (2u << 20) ? base / 2 : base * 3 / 2));
+  }
   // light-weight blocks (128 channels): the cluster kernels move 4u / 6u and, with their weight slices in shared memory,
   // win both directions (128x28^2 forward at batch 1024: 0.357 ms vs 0.381 ms through the pipeline's 56 KB items)
   return !bwd && g_tile_light_fwd && u >= ((size_t)g_tile_min_mb_light << 20);

@@ -30,7 +30,10 @@ def main():
            "`old` = round-1 paths (tunable `tile_kind=2`): cluster kernels for 128x28^2 / 256x14^2, streaming plane kernels + batched GEMMs",
            "for 512x7^2. `auto` = shipped selection. Variants starting with another letter force the tile pipeline with the tunables",
            "named in `scripts/sweep.py`. The backward column includes the weight-gradient GEMM launch that follows the block's kernel.", ""]
-    doc += table(load("r2_sweep_pol2.json"), title="Shipped selection vs round-1 paths")
+    doc += table(load("r2_sweep_final.json"), title="Final selection at the end of round 2 (`auto`) vs cluster / streaming kernels only (`old` = `tile_kind=2`) vs pipeline forced (`sw_tile`)",
+                 note="After the second half of round 2 (`profiles/r2_cluster_kernels.md`): cluster kernels with the FC weights in shared memory and the "
+                      "st.async exchange, weight-gradient GEMMs inside the backward pipeline launch.")
+    doc += table(load("r2_sweep_pol2.json"), title="Mid-round selection vs round-1 paths (before the cluster-kernel work)")
     doc += table(load("r2_sweep_f.json"), title="Forward chunk size (f_c28 / f_c56 / f_c100 = 28 / 56 / 100 KB items), tile pipeline forced",
                  note="56 KB wins from ~190 MB per modality, 28 KB below; `old` rows show where the pipeline starts to pay.")
     doc += table(load("r2_sweep_t.json") + load("r2_sweep_c.json") + load("r2_sweep_s.json"),
