@@ -144,6 +144,19 @@ struct TileParams {
   int nodeps;                // measurement only: S items skip their dependency wait (results are garbage)
   long long* stats;          // debug (tunable "tile_stats_ptr"): 16 clock64 sums per CTA, or nullptr
 };
+// Measurement hooks (cycle breakdowns, the timeline trace, the stage-isolation modes of scripts/sweep.py) are compiled in
+// only with -DGML_TILE_TRACE (make EXTRA=-DGML_TILE_TRACE): the loader warp runs ~1000 dependent cycles per item, every
+// instruction in its loop counts.
+#ifdef GML_TILE_TRACE
+#define TILE_STATS(P) ((P).stats)
+#define TILE_NODEPS(P) ((P).nodeps)
+#define TILE_TRACE_ONLY(P) ((P).trace_only)
+#else
+#define TILE_STATS(P) (static_cast<long long*>(nullptr))
+#define TILE_NODEPS(P) 0
+#define TILE_TRACE_ONLY(P) 0
+#endif
+
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -280,7 +293,7 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
     seg_t = (seg & 1) ? (seg >> 1) - P.lag : (seg >> 1);
     if (seg_t < 0 || seg_t >= T) { seg_chunks = 0; return; }
     // measurement only: 5 = R stage alone, 6 = S stage alone (no GEMM work, no dependencies; results are garbage)
-    if (((P.nodeps == 5 || P.nodeps == 7) && seg_kind == kItemS) || ((P.nodeps == 6 || P.nodeps == 8) && seg_kind == kItemR)) { seg_chunks = 0; return; }
+    if (((TILE_NODEPS(P) == 5 || TILE_NODEPS(P) == 7) && seg_kind == kItemS) || ((TILE_NODEPS(P) == 6 || TILE_NODEPS(P) == 8) && seg_kind == kItemR)) { seg_chunks = 0; return; }
     seg_chunks = (unsigned)(tile_rows(P, seg_t) * P.cps);
     seg_end = seg_start + 2u * seg_chunks;
     seg_n0 = seg_t * P.m_tile;
@@ -331,7 +344,7 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
     while (flush_tile < T && (exhausted || seg > 2 * flush_tile) && (fin & 0xffffull) == (iss & 0xffffull)) {
       const unsigned cnt = (unsigned)(iss & 0xffffull);
       if (cnt && lane == 0) red_release_add(tile_ctr(P, flush_tile) + 0, cnt);
-      if (cnt && lane == 0 && flush_tile < 64) trace_max(P.stats, kTraceTileRow + flush_tile, 1);
+      if (cnt && lane == 0 && flush_tile < 64) trace_max(TILE_STATS(P), kTraceTileRow + flush_tile, 1);
       iss >>= 16; fin >>= 16;
       ++flush_tile;
     }
@@ -377,7 +390,7 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
       const unsigned ch = idx - (mod ? seg_chunks : 0u);
       const int q0 = seg_qbase + (int)ch * P.p;
       if (seg_kind == kItemS && seg_t > ready_tile) {
-        if (!P.nodeps) {
+        if (!TILE_NODEPS(P)) {
           bool ok = ld_acquire_u32(tile_ctr(P, seg_t) + 2) >= need_f2;
           ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
           if (!ok) {
@@ -388,7 +401,7 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
           }
         }
         ready_tile = seg_t;
-        if (lane == 0 && seg_t < 64) trace_max(P.stats, kTraceTileRow + seg_t, 2);
+        if (lane == 0 && seg_t < 64) trace_max(TILE_STATS(P), kTraceTileRow + seg_t, 2);
         asm volatile("fence.proxy.async;" ::: "memory");  // the gates were written through the generic proxy
       }
       const long long t2 = timing ? clk() : 0;
@@ -433,12 +446,12 @@ __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMet
         bulk_g2s_elect(sgate, P.gate[mod] + q0, vec_bytes, bar, pol_drop);
         if (P.bwd) bulk_g2s_elect(sgate + vec_bytes, P.add[mod] + q0, vec_bytes, bar, pol_drop);
       }
-      if (lane == 0 && P.stats && seg_t < 64 && idx == 0) {  // first chunk of a segment only: keeps the trace cheap
-        if (seg_kind == kItemR) trace_min(P.stats, kTraceTileRow + seg_t, 0);
-        else trace_min(P.stats, kTraceTileRow + seg_t, 3);
+      if (lane == 0 && TILE_STATS(P) && seg_t < 64 && idx == 0) {  // first chunk of a segment only: keeps the trace cheap
+        if (seg_kind == kItemR) trace_min(TILE_STATS(P), kTraceTileRow + seg_t, 0);
+        else trace_min(TILE_STATS(P), kTraceTileRow + seg_t, 3);
       }
-      if (lane == 0 && P.stats && seg_t < 64 && seg_kind == kItemS && ticket + 1 == seg_end)
-        trace_max(P.stats, kTraceTileRow + seg_t, 4);
+      if (lane == 0 && TILE_STATS(P) && seg_t < 64 && seg_kind == kItemS && ticket + 1 == seg_end)
+        trace_max(TILE_STATS(P), kTraceTileRow + seg_t, 4);
       ++uses;
       if (++slot == P.slots) slot = 0;
       if (timing) { t_prev = clk(); c_issue += t_prev - t2; }
@@ -540,7 +553,7 @@ __device__ __forceinline__ void reduce_chunk_t(const TileParams& P, const SlotMe
       t0 += __shfl_xor_sync(0xffffffffu, t0, o);
       t1 += __shfl_xor_sync(0xffffffffu, t1, o);
     }
-    if (lane_in == 0 && (P.nodeps != 4 || t0 == 123.456f)) {
+    if (lane_in == 0 && (TILE_NODEPS(P) != 4 || t0 == 123.456f)) {
       if (BWD) {
         // dE = dg * g (1 - g); with the weight gradients folded in, also dE^T[channel][sample] (one 4-byte store per
         // plane: ~N*2C stores per launch, absorbed by L2)
@@ -602,7 +615,7 @@ __device__ __forceinline__ void scale_chunk_t(const TileParams& P, const SlotMet
       } else {
         x[u].x *= sgate[p0] * gs; x[u].y *= sgate[p1] * gs; x[u].z *= sgate[p2] * gs; x[u].w *= sgate[p3] * gs;
       }
-      if (P.nodeps != 4) stg_hint(o + i, x[u], pol_out);
+      if (TILE_NODEPS(P) != 4) stg_hint(o + i, x[u], pol_out);
       else if (x[u].x == 123.456f) stg_stream(o + i, x[u]);
     }
   }
@@ -627,8 +640,8 @@ __device__ void stream_workers(const TileParams& P, const StreamSmem& sm, const 
     const long long t1 = timing ? clk() : 0;
     const SlotMeta m = metas[slot];
     if (m.kind == kItemStop) break;
-    if (P.nodeps == 2 || P.nodeps == 3 || P.nodeps >= 7) {  // measurement only (7 / 8: R / S stage alone, loads only): no compute, just recycle the slot
-      if (P.nodeps == 3 && lane == 0) { volatile float sink = sm.chunk(slot, 0)[tid]; (void)sink; }
+    if (TILE_NODEPS(P) == 2 || TILE_NODEPS(P) == 3 || TILE_NODEPS(P) >= 7) {  // measurement only (7 / 8: R / S stage alone, loads only): no compute, just recycle the slot
+      if (TILE_NODEPS(P) == 3 && lane == 0) { volatile float sink = sm.chunk(slot, 0)[tid]; (void)sink; }
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(&empty[slot]);
     } else if (m.kind == kItemR) {
@@ -1017,7 +1030,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     if (tid == 0) s_ticket = atomicAdd(&P.ctr[1], 1u);
     __syncthreads();
     const unsigned ticket = s_ticket;
-    if (ticket >= total || P.nodeps >= 5) break;
+    if (ticket >= total || TILE_NODEPS(P) >= 5) break;
     if (ticket >= t_cs && ticket < t_post) {
       // ---- column-sum item: needs every tile's R, F1 and F2 -----------------------------------------------------
       if (tid == 0) {
@@ -1055,7 +1068,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     it.split = rr - it.ntile * g.splits;
     unsigned* tc = tile_ctr(P, it.stage < 2 ? it.tile : 0);
     const long long tg0 = timing ? clk() : 0;
-    const unsigned long long t_item0 = (tid == 0 && P.stats) ? global_ns() : 0ull;
+    const unsigned long long t_item0 = (tid == 0 && TILE_STATS(P)) ? global_ns() : 0ull;
     if (tid == 0) {
       if (P.w_cat_t) wait_counter(&P.ctr[3], (unsigned)P.n_gemm);
       if (it.stage >= 2) {
@@ -1083,14 +1096,14 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
     const int k_end = min(g.k_total, k_begin + g.k_per_split);
     const int nk = k_end > k_begin ? (k_end - k_begin + UK - 1) / UK : 0;
     const long long tg1 = timing ? clk() : 0;
-    if (tid == 0 && P.stats && ticket < 256) {
-      long long* row = P.stats + (size_t)(kTraceGemmRow + ticket) * 16;
+    if (tid == 0 && TILE_STATS(P) && ticket < 256) {
+      long long* row = TILE_STATS(P) + (size_t)(kTraceGemmRow + ticket) * 16;
       row[0] = it.tile; row[1] = it.stage; row[2] = it.ntile; row[3] = grank; row[4] = (long long)t_item0; row[5] = (long long)global_ns();
     }
     gemm_item_mainloop(P, g, it, u_smem, bars, tmem, kbase, gbase, nk, sum, warp, lane, tid,
-                       st_cycles ? P.stats + (size_t)(gridDim.x + blockIdx.x) * 16 : nullptr);
+                       st_cycles ? TILE_STATS(P) + (size_t)(gridDim.x + blockIdx.x) * 16 : nullptr);
     const long long tg2 = timing ? clk() : 0;
-    if (tid == 0 && P.stats && ticket < 256) P.stats[(size_t)(kTraceGemmRow + ticket) * 16 + 6] = (long long)global_ns();
+    if (tid == 0 && TILE_STATS(P) && ticket < 256) TILE_STATS(P)[(size_t)(kTraceGemmRow + ticket) * 16 + 6] = (long long)global_ns();
     kbase += (uint32_t)nk;
     gbase += (uint32_t)((nk + UGROUP - 1) / UGROUP);
 
@@ -1148,7 +1161,7 @@ __device__ void gemm_role(const TileParams& P, int grank, unsigned char* u_smem,
         else { st_cycles[14] += tg5 - tg4; st_cycles[15] += t6 - tg5; }
       }
       if (tid == 0 && it.stage < 2) red_release_add(tc + 1 + it.stage, 1u);
-      if (tid == 0 && P.stats && ticket < 256) P.stats[(size_t)(kTraceGemmRow + ticket) * 16 + 7] = (long long)global_ns();
+      if (tid == 0 && TILE_STATS(P) && ticket < 256) TILE_STATS(P)[(size_t)(kTraceGemmRow + ticket) * 16 + 7] = (long long)global_ns();
     }
     if (timing) {
       const long long tg6 = clk();
@@ -1179,9 +1192,9 @@ __global__ void __launch_bounds__(kThreads, 1) tile_pipeline_kernel(const __grid
   if (tid == 0) s_role = atomicAdd(&P.ctr[2], 1u);
   __syncthreads();
   const int role = (int)s_role;
-  long long* st_cycles = (P.stats && !P.trace_only) ? P.stats + (size_t)blockIdx.x * 16 : nullptr;
+  long long* st_cycles = (TILE_STATS(P) && !TILE_TRACE_ONLY(P)) ? TILE_STATS(P) + (size_t)blockIdx.x * 16 : nullptr;
   const long long t_begin = st_cycles ? clk() : 0;
-  if (tid == 0) trace_min(P.stats, kTraceStartRow, 0);
+  if (tid == 0) trace_min(TILE_STATS(P), kTraceStartRow, 0);
   if (role < P.n_gemm) {
     gemm_role(P, role, smem, tid, st_cycles);
     if (st_cycles && tid == 0) { st_cycles[0] = 1; st_cycles[7] = clk() - t_begin; }
