@@ -96,8 +96,9 @@ int gml_profile_read(int tag, double* total_ms, int64_t* launches);
  *   "fused_kind"     0 auto | 1 shared-memory-resident cluster kernels | 2 L2-resident cluster kernels
  *   "fused_cluster"  0 auto | 4 | 8 | 16 CTAs per cluster
  *   "fused_threads"  0 auto | 256 | 512
- *   "fused_occ", "fused_stash_kb", "fused_group_kb", "fused_prefetch", "fused_weight_ratio_x100"
- *                    occupancy / stash / group size / L2 prefetch distance / path-selection threshold
+ *   "fused_occ", "fused_stash_kb", "fused_group_kb", "fused_weight_ratio_x100"
+ *                    occupancy / stash / group size / path-selection threshold ("fused_prefetch" is accepted and ignored)
+ *   "fused_wsmem"    -1 auto | bit 0 / bit 1: first / second FC's weight slice of a CTA lives in shared memory
  *   "gemm_umma"      1 tcgen05 (TMEM) 3xTF32 kernel for FC problems above ~1e8 MACs | 0 never
  *   "gemm_tf32x3"    1 mma.sync 3xTF32 for large problems the tcgen05 kernel does not take | 0 CUDA cores
  *   "gemm_big_tiles" 1 opt-in 128x128 CUDA-core tiles
@@ -105,8 +106,12 @@ int gml_profile_read(int tag, double* total_ms, int64_t* launches);
  *   "tile_lag", "tile_m", "tile_gemm_ctas", "tile_chunk_kb", "tile_min_mb"
  *                    pipeline depth in tiles / samples per tile / CTAs on the FC role / chunk size /
  *                    smallest feature map (MB per modality) that takes the tile pipeline automatically
+ *   "tile_wgrad"     1 weight-gradient GEMMs inside the backward pipeline launch | 0 separate launch
+ *   "tile_light_fwd" 1 forward of blocks with < 1 MB of FC weights on the pipeline from "tile_min_mb_light" on | 0 never
  *   "overlap_wgrad"  1 weight-gradient GEMMs on the library's side stream (streaming backward)
- *   "fused_trace_ptr", "gemm_trace_ptr"  device buffers for per-phase timing stamps (debug)        */
+ *   "fused_trace_ptr", "fused_occ_trace_ptr", "tile_stats_ptr", "gemm_trace_ptr"
+ *                    device buffers for timing stamps; the first three only act in a tracing build
+ *                    (make EXTRA="-DGML_L2_TRACE -DGML_TILE_TRACE")                                  */
 int gml_set_tunable(const char* name, int64_t value);
 
 /* ---------------------------------------------------------------------------------------
