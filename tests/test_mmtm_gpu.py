@@ -229,6 +229,37 @@ def test_fused_cluster_kernels_vs_oracle(shape, fused_geometry):
         assert torch.equal(r[k], r3[k]), k
 
 
+@pytest.mark.parametrize("wsm", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(5, 64, 6, 6), (7, 128, 28, 28), (33, 128, 8, 8)], ids=lambda s: "n%dc%d_%dx%d" % s)
+@pytest.mark.parametrize("cs", [4, 8])
+def test_l2_cluster_kernels_weight_slices_in_shared_memory(shape, wsm, cs):
+    """Every combination of 'FC weight slice in shared memory / in global memory' (tunable fused_wsmem: bit 0 = first FC,
+    bit 1 = second FC; the default picks 3 when both fit) against the oracle, both cluster sizes."""
+    n, c, h, w = shape
+    lib = _lib.load()
+    rs = np.random.RandomState(n * 11 + c + wsm)
+    t = lambda *s: torch.from_numpy(rs.standard_normal(s).astype(np.float32))
+    x = dict(A=t(n, c, h, w), B=t(n, c, h, w), gA=t(n, c, h, w), gB=t(n, c, h, w))
+    p = mo.synth_params(c + n + wsm, c, c)
+    _lib.check(lib.gml_set_tunable(b"fused_kind", 2))
+    _lib.check(lib.gml_set_tunable(b"fused_cluster", cs))
+    _lib.check(lib.gml_set_tunable(b"fused_wsmem", wsm))
+    try:
+        m = make_module(c, c, p, _lib.F_FORCE_FUSED)
+        before = lib.gml_launch_count(6) + lib.gml_launch_count(7)
+        r = run_cuda(m, x, 0)
+        assert lib.gml_launch_count(6) + lib.gml_launch_count(7) == before + 2
+    finally:
+        _lib.check(lib.gml_set_tunable(b"fused_kind", 0))
+        _lib.check(lib.gml_set_tunable(b"fused_cluster", 0))
+        _lib.check(lib.gml_set_tunable(b"fused_wsmem", -1))
+    st = mo.MMTMState.zeros(c)
+    o = mo.forward_backward(x["A"], x["B"], p, st, x["gA"], x["gB"], 0)
+    for k in ["A_out", "B_out", "dA", "dB", "gA", "gB", "sA", "sB", "dWsq", "dbsq", "dWv", "dbv", "dWs", "dbs"]:
+        assert_close(r[k], o[k], 1e-5, k)
+    assert_close(r["run_v"], st.run_v, 1e-6, "run_v")
+
+
 def test_force_fused_fails_loudly_when_unsupported():
     m = make_module(24, 24, mo.synth_params(1, 24, 24), _lib.F_FORCE_FUSED)
     a = torch.randn(2, 24, 5, 5, device=DEV)
