@@ -54,7 +54,7 @@ int g_tile_ksplit_tiles = 0;  // tunable "tile_ksplit_tiles": k-tiles per split-
                             // chain latency, and partial planes + folds cost more GEMM-CTA time than they save)
 int g_tile_switch = 1;      // tunable "tile_switch": GEMM CTAs join the stream role once the GEMM tickets are exhausted
 int g_tile_trace_only = 0;  // tunable "tile_trace_only" (with tile_stats_ptr): timeline rows only
-int g_tile_rpol = 0;        // tunable "tile_rpol": L2 policy of the R-stage reads (0 evict_last, 1 evict_first, 2 evict_normal)
+int g_tile_rpol = 0;        // tunable "tile_rpol": L2 policy of the R-stage reads (0 auto: forward evict_last, backward evict_first; 1 evict_first, 2 evict_normal, 3 evict_last)
 int g_tile_max_slots = 0;   // tunable "tile_max_slots": cap on the slot ring (0 = as many as fit)
 int g_tile_split_copies = 1;
 int g_tile_draw = 4;        // tunable "tile_draw": stream tickets per draw (two draws are kept in flight)
@@ -277,7 +277,11 @@ __device__ __forceinline__ void mbar_expect_tx_el(uint32_t bar, uint32_t bytes) 
 __device__ void stream_loader(const TileParams& P, const StreamSmem& sm, SlotMeta* metas, uint64_t* full, uint64_t* empty,
                               long long* st_cycles, int lane) {
   const uint64_t pol_drop = policy_evict_first();
-  const uint64_t pol_keep = P.rpol == 0 ? policy_evict_last() : (P.rpol == 1 ? pol_drop : policy_evict_normal());
+  // R-stage reads: the forward asks L2 to keep them (a late S item of the same tile sometimes still hits); the backward's
+  // S stage never does, and evict_last lines only push the GEMM operands (Z, dE, weights) out: 512x7^2 backward
+  // 0.222 -> 0.208 ms with evict_first (profiles/r2_sweep.md).  rpol: 0 = this rule, 1 evict_first, 2 normal, 3 evict_last
+  const uint64_t pol_keep = P.rpol == 0 ? (P.bwd ? pol_drop : policy_evict_last())
+                                        : (P.rpol == 1 ? pol_drop : (P.rpol == 2 ? policy_evict_normal() : policy_evict_last()));
   const int T = P.n_tiles, nseg = 2 * (T + P.lag);
   const uint32_t smem0 = u_smem_addr(sm.base), full0 = u_smem_addr(full);
   const uint32_t vec_bytes = (uint32_t)P.p * 4u;
@@ -1448,7 +1452,8 @@ bool tile_preferred(int n, int c, int hw, int d, bool bwd) {
   // from 1.5x of it -- its cluster kernel still wins at batch 512 (0.126 vs 0.133 ms) and loses at 1024 (0.290 vs 0.205)
   if (w_bytes >= (1u << 20)) {
     const size_t base = (size_t)g_tile_min_mb << 20;
-    return u >= (bwd ? base : (w_bytes >= (2u << 20) ? base / 2 : base * 3 / 2));
+    // backward: from half the threshold for both (256x14^2 at batch 256: 0.120 vs 0.126 ms, 512x7^2 at 512: 0.155 vs 0.168)
+    return u >= (bwd ? base / 2 : (w_bytes >= (2u << 20) ? base / 2 : base * 3 / 2));
   }
   // light-weight blocks (128 channels): the cluster kernels move 4u / 6u and, with their weight slices in shared memory,
   // win both directions (128x28^2 forward at batch 1024: 0.357 ms vs 0.381 ms through the pipeline's 56 KB items)

@@ -54,6 +54,9 @@ VARIANTS = {
     "q_rload_c56": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_chunk_kb": 56}),
     "q_rload_c14": (L.F_FORCE_TILE, {"tile_nodeps": 7, "tile_chunk_kb": 14}),
     "s_slots4": (L.F_FORCE_TILE, {"tile_max_slots": 4}),
+    "d_draw2": (L.F_FORCE_TILE, {"tile_draw": 2}),
+    "d_draw8": (L.F_FORCE_TILE, {"tile_draw": 8}),
+    "d_draw16": (L.F_FORCE_TILE, {"tile_draw": 16}),
     "s_slots2": (L.F_FORCE_TILE, {"tile_max_slots": 2}),
     "s_slots4_c14": (L.F_FORCE_TILE, {"tile_max_slots": 4, "tile_chunk_kb": 14}),
     "s_slots8_c14": (L.F_FORCE_TILE, {"tile_max_slots": 8, "tile_chunk_kb": 14}),
