@@ -488,10 +488,12 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
   // with an ordered fold: deterministic, no atomics)
   bool bias_done = false;   // the tile pipeline forms the bias gradients itself
   bool wgrad_tiled = false; // ... and, when all three are requested, the weight gradients too
-  auto weight_grads = [&](cudaStream_t ws_stream, void* ws_mem) -> int {
+  // part: 1 = the weight-gradient GEMMs, 2 = the bias gradients (column sums), 3 = both
+  auto weight_grads = [&](cudaStream_t ws_stream, void* ws_mem, int part = 3) -> int {
     GemmDesc gw[3];
     int cw = 0;
     if (wgrad_tiled) return GML_OK;
+    if (!(part & 1)) goto bias_part;
     if (d_w_v) {
       if (la) gw[cw++] = GemmDesc{de_a, h, d_w_v, nullptr, nullptr, d.c_v, d.d, d.n, d.c_v, d.d, d.d, 0, 0, 0, kActNone, 0};
       else GML_TRY(launch_fill_zero(d_w_v, (size_t)d.c_v * d.d, ws_stream));
@@ -510,7 +512,8 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
       }
     }
     if (cw) GML_TRY(launch_gemm(gw, cw, ws_stream, ws_mem, gws_bytes));
-    if (bias_done) return GML_OK;
+  bias_part:
+    if (bias_done || !(part & 2)) return GML_OK;
     ColsumSeg segs[3];
     int nseg = 0;
     if (d_b_v) {
@@ -630,7 +633,21 @@ extern "C" int gml_mmtm_bwd(const float* go_a, const float* go_b, const float* a
     }
   }
 
-  if (!wgrad_done) GML_TRY(weight_grads(st, gws));
+  if (!wgrad_done) {
+    // after a cluster kernel: the bias-gradient column sums run on the side stream next to the weight-gradient GEMMs
+    // (two ~10 us launches that only share read-only inputs)
+    SideStream* side = (fused_done && !bias_done && g_overlap_wgrad.load()) ? side_stream() : nullptr;
+    if (side) {
+      GML_CUDA_TRY(cudaEventRecord(side->fork, st));
+      GML_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      GML_TRY(weight_grads(side->stream, gws2, 2));
+      GML_CUDA_TRY(cudaEventRecord(side->join, side->stream));
+      GML_TRY(weight_grads(st, gws, 1));
+      GML_CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
+    } else {
+      GML_TRY(weight_grads(st, gws));
+    }
+  }
   return GML_OK;
 }
 
