@@ -271,7 +271,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "fused_weight_ratio_x100")) { g_fused_weight_ratio_x100 = (int)value; return GML_OK; }
   if (!strcmp(name, "overlap_wgrad")) { g_overlap_wgrad.store(value ? 1 : 0); return GML_OK; }
   if (!strcmp(name, "fused_wsmem")) { g_fused_wsmem = value < 0 ? -1 : (int)(value & 3); return GML_OK; }
-  if (!strcmp(name, "fused_stash_kb")) { g_fused_stash_kb = value < 0 ? 0 : (value > 200 ? 200 : (int)value); return GML_OK; }
+  if (!strcmp(name, "fused_stash_kb")) { g_fused_stash_kb = value < 0 ? -1 : (value > 200 ? 200 : (int)value); return GML_OK; }
   if (!strcmp(name, "fused_group_kb")) { g_fused_group_kb = (int)value; return GML_OK; }
   if (!strcmp(name, "gemm_big_tiles")) { g_gemm_big_tiles = value ? 1 : 0; return GML_OK; }
   if (!strcmp(name, "gemm_tf32x3")) { g_gemm_tf32x3 = value ? 1 : 0; return GML_OK; }

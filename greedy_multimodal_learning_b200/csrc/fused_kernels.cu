@@ -43,7 +43,8 @@ int g_fused_threads = 0;
 int g_fused_kind = 0;      // 0 auto, 1 shared-memory resident, 2 L2 resident
 int g_fused_occ = 4;       // L2-resident kernels: CTAs per SM the register budget is compiled for (4: 64 regs, 5: 48)
 int g_fused_group_kb = 128;  // L2-resident kernels: take 2 samples per cluster while 2 slices <= this many KB per CTA
-int g_fused_stash_kb = 24; // L2-resident kernels: shared memory per CTA used to stash planes between the passes (24 KB measured best; 46+ costs occupancy)
+int g_fused_stash_kb = -1; // L2-resident kernels: shared memory per CTA used to stash planes between the passes; -1 = automatic:
+                           // 24 KB (measured best; 46+ costs occupancy), none for a backward that has its weights in shared memory
 int g_fused_wsmem = -1;    // L2-resident kernels: FC weight slices prefetched into shared memory (cp.async, hidden behind pass 1);
                            // -1 auto (whatever fits at 4 CTAs per SM), else bit 0 = first FC, bit 1 = second FC
 int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch look-ahead distance in groups (0 = off)
@@ -997,7 +998,10 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
 #undef GML_STAMP2
 }
 
-template <int T, int L, int GMAX, int OCC>
+// STASH = false: no per-thread stash code in the streaming loops at all.  The loops are issue-bound (57 % of the issue
+// slots busy), and with the weight slices in shared memory the backward gains more from the shorter loops than it loses
+// in L2 re-reads (8-CTA clusters, batch 1024: 0.461 -> 0.451 ms); the forward keeps its stash (0.314 vs 0.321 ms).
+template <int T, int L, int GMAX, int OCC, bool STASH>
 __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, const FusedCfg f) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -1076,7 +1080,7 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const float4* gv = reinterpret_cast<const float4*>((mod ? a.go_b : a.go_a) + off);
     const float4* xv = reinterpret_cast<const float4*>((mod ? a.b : a.a) + off);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const bool kept = p < f.keep_planes;
+    const bool kept = STASH && p < f.keep_planes;
     const uint64_t polg = kept ? pol_drop : pol_keep;
     for (int i0 = 0; i0 < hw4; i0 += 4 * L) {
       float4 x[4], gg[4];
@@ -1206,7 +1210,7 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
     const size_t off = ((size_t)(n0 + g) * f.c + (size_t)rank * f.cq + cl) * f.hw;
     const float4* gv = reinterpret_cast<const float4*>((mod ? a.go_b : a.go_a) + off);
     float4* o = reinterpret_cast<float4*>((mod ? a.d_b : a.d_a) + off);
-    const bool kept = p < f.keep_planes;
+    const bool kept = STASH && p < f.keep_planes;
     for (int i0 = 0; i0 < hw4; i0 += 8 * L) {
       float4 x[8];
 #pragma unroll
@@ -1262,7 +1266,7 @@ bool make_cfg_l2(int n, int c, int hw, int d, int cs, bool bwd, FusedCfg* out) {
   int mask = g_fused_wsmem;
   if (mask < 0) mask = (small + w1 + w2 + 8 * 1024 <= lim4) ? 3 : 0;
   const size_t wbytes = ((mask & 1) ? w1 : 0) + ((mask & 2) ? w2 : 0);
-  size_t stash = (size_t)g_fused_stash_kb * 1024;
+  size_t stash = g_fused_stash_kb >= 0 ? (size_t)g_fused_stash_kb * 1024 : ((bwd && (mask & 3) == 3) ? 0 : 24 * 1024);
   if (wbytes) {
     size_t lim = lim4;
     if (small + wbytes > lim) lim = 75 * 1024;    // 3 CTAs per SM
@@ -1326,8 +1330,9 @@ int dispatch_l2_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
   const int l = lanes_for(f.hw);
 #define GML_L2B(LL, GG)                                                                              \
   do {                                                                                               \
-    if (g_fused_occ == 5) return do_launch_l2(l2_bwd_kernel<256, LL, GG, 5>, args, f, true, st, kTagFusedBwd); \
-    return do_launch_l2(l2_bwd_kernel<256, LL, GG, 4>, args, f, true, st, kTagFusedBwd);              \
+    if (f.keep_planes == 0) return do_launch_l2(l2_bwd_kernel<256, LL, GG, 4, false>, args, f, true, st, kTagFusedBwd); \
+    if (g_fused_occ == 5) return do_launch_l2(l2_bwd_kernel<256, LL, GG, 5, true>, args, f, true, st, kTagFusedBwd); \
+    return do_launch_l2(l2_bwd_kernel<256, LL, GG, 4, true>, args, f, true, st, kTagFusedBwd);        \
   } while (0)
   if (f.g == 1) { if (l == 32) GML_L2B(32, 1); if (l == 16) GML_L2B(16, 1); GML_L2B(8, 1); }
   if (l == 32) GML_L2B(32, 2);
