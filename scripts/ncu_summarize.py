@@ -27,7 +27,7 @@ def raw(rep):
         d = {"name": r[h.index("Kernel Name")]}
         for m in M:
             hm = [x for x in h if x == m or x.endswith("." + m)]
-            hm = [x for x in hm if r[h.index(x)] != ""]
+            hm = [x for x in hm if r[h.index(x)] not in ("", "no data", "n/a")]
             if hm:
                 v = float(r[h.index(hm[0])].replace(",", ""))
                 d[m] = v * UNIT.get(units[h.index(hm[0])], 1.0)
