@@ -252,6 +252,7 @@ extern int g_fused_weight_ratio_x100;
 extern int g_fused_group_kb;
 extern int g_fused_stash_kb;
 extern int g_fused_wsmem;
+extern int g_fused_hw_special;
 extern int g_sq_variant;
 extern int g_tile_kind, g_tile_lag, g_tile_gemm_ctas, g_tile_m, g_tile_chunk_kb, g_tile_min_mb;
 extern long long* g_tile_stats;
@@ -270,6 +271,7 @@ extern "C" int gml_set_tunable(const char* name, int64_t value) {
   }
   if (!strcmp(name, "fused_weight_ratio_x100")) { g_fused_weight_ratio_x100 = (int)value; return GML_OK; }
   if (!strcmp(name, "overlap_wgrad")) { g_overlap_wgrad.store(value ? 1 : 0); return GML_OK; }
+  if (!strcmp(name, "fused_hw_special")) { g_fused_hw_special = value != 0; return GML_OK; }
   if (!strcmp(name, "fused_wsmem")) { g_fused_wsmem = value < 0 ? -1 : (int)(value & 3); return GML_OK; }
   if (!strcmp(name, "fused_stash_kb")) { g_fused_stash_kb = value < 0 ? -1 : (value > 200 ? 200 : (int)value); return GML_OK; }
   if (!strcmp(name, "fused_group_kb")) { g_fused_group_kb = (int)value; return GML_OK; }

@@ -45,6 +45,7 @@ int g_fused_occ = 4;       // L2-resident kernels: CTAs per SM the register budg
 int g_fused_group_kb = 128;  // L2-resident kernels: take 2 samples per cluster while 2 slices <= this many KB per CTA
 int g_fused_stash_kb = -1; // L2-resident kernels: shared memory per CTA used to stash planes between the passes; -1 = automatic:
                            // 24 KB (measured best; 46+ costs occupancy), none for a backward that has its weights in shared memory
+int g_fused_hw_special = 1;  // L2-resident kernels: 1 = plane-size-specialised instantiation for 28 x 28 planes (tunable "fused_hw_special")
 int g_fused_wsmem = -1;    // L2-resident kernels: FC weight slices prefetched into shared memory (cp.async, hidden behind pass 1);
                            // -1 auto (whatever fits at 4 CTAs per SM), else bit 0 = first FC, bit 1 = second FC
 int g_fused_prefetch = 0;  // L2-resident kernels: bulk L2 prefetch look-ahead distance in groups (0 = off)
@@ -806,7 +807,10 @@ __device__ __forceinline__ void occ_stamp(const FusedCfg& f, int slot) {
   }
 }
 
-template <int T, int L, int GMAX, int OCC>
+// HW4C != 0: the plane size (in float4) is a compile-time constant -- for 28 x 28 planes (196 vectors, 32 lanes per plane) six
+// of the eight load slots of a lane are then unconditionally valid, one is valid for lanes 0-3 and one never: their
+// predicates, and the instructions of the dead slot, fold away in the issue-bound streaming loops.
+template <int T, int L, int GMAX, int OCC, int HW4C = 0>
 __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, const FusedCfg f) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -853,7 +857,7 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
 
   constexpr int kPlanesPerPass = T / L;
   const int lane = tid % L, grp_in_pass = tid / L;
-  const int hw4 = f.hw >> 2;
+  const int hw4 = HW4C ? HW4C : (f.hw >> 2);
   const int n0 = grp * f.g;
   const int gcount = min(f.g, f.n - n0);
   const int vplanes = gcount * 2 * f.cq;
@@ -1001,7 +1005,7 @@ __global__ void __launch_bounds__(T, OCC) l2_fwd_kernel(const FusedFwdArgs a, co
 // STASH = false: no per-thread stash code in the streaming loops at all.  The loops are issue-bound (57 % of the issue
 // slots busy), and with the weight slices in shared memory the backward gains more from the shorter loops than it loses
 // in L2 re-reads (8-CTA clusters, batch 1024: 0.461 -> 0.451 ms); the forward keeps its stash (0.314 vs 0.321 ms).
-template <int T, int L, int GMAX, int OCC, bool STASH>
+template <int T, int L, int GMAX, int OCC, bool STASH, int HW4C = 0>
 __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, const FusedCfg f) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -1028,7 +1032,7 @@ __global__ void __launch_bounds__(T, OCC) l2_bwd_kernel(const FusedBwdArgs a, co
   const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
   constexpr int kPlanesPerPass = T / L;
   const int lane = tid % L, grp_in_pass = tid / L;
-  const int hw4 = f.hw >> 2;
+  const int hw4 = HW4C ? HW4C : (f.hw >> 2);
   const int ncol_h = f.dq, ncol_z = 2 * f.cq;
   const int n0 = grp * f.g;
   const int gcount = min(f.g, f.n - n0);
@@ -1319,6 +1323,8 @@ int dispatch_l2_fwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
     if (g_fused_occ == 5) return do_launch_l2(l2_fwd_kernel<256, LL, GG, 5>, args, f, false, st, kTagFusedFwd); \
     return do_launch_l2(l2_fwd_kernel<256, LL, GG, 4>, args, f, false, st, kTagFusedFwd);             \
   } while (0)
+  if (g_fused_hw_special && l == 32 && f.hw == 784 && f.g == 1 && g_fused_occ != 5)   // 28 x 28 planes
+    return do_launch_l2(l2_fwd_kernel<256, 32, 1, 4, 196>, args, f, false, st, kTagFusedFwd);
   if (f.g == 1) { if (l == 32) GML_L2F(32, 1); if (l == 16) GML_L2F(16, 1); GML_L2F(8, 1); }
   if (l == 32) GML_L2F(32, 2);
   if (l == 16) GML_L2F(16, 2);
@@ -1334,6 +1340,10 @@ int dispatch_l2_bwd(const Args& args, const FusedCfg& f, cudaStream_t st) {
     if (g_fused_occ == 5) return do_launch_l2(l2_bwd_kernel<256, LL, GG, 5, true>, args, f, true, st, kTagFusedBwd); \
     return do_launch_l2(l2_bwd_kernel<256, LL, GG, 4, true>, args, f, true, st, kTagFusedBwd);        \
   } while (0)
+  if (g_fused_hw_special && l == 32 && f.hw == 784 && f.g == 1 && g_fused_occ != 5) {
+    if (f.keep_planes == 0) return do_launch_l2(l2_bwd_kernel<256, 32, 1, 4, false, 196>, args, f, true, st, kTagFusedBwd);
+    return do_launch_l2(l2_bwd_kernel<256, 32, 1, 4, true, 196>, args, f, true, st, kTagFusedBwd);
+  }
   if (f.g == 1) { if (l == 32) GML_L2B(32, 1); if (l == 16) GML_L2B(16, 1); GML_L2B(8, 1); }
   if (l == 32) GML_L2B(32, 2);
   if (l == 16) GML_L2B(16, 2);

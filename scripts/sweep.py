@@ -110,6 +110,7 @@ VARIANTS = {
     "old_cs8_ws3_st8": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_wsmem": 3, "fused_stash_kb": 8}),
     "old_cs8_ws3_st0": (0, {"tile_kind": 2, "fused_cluster": 8, "fused_wsmem": 3, "fused_stash_kb": 0}),
     "light_tile": (0, {"tile_light_fwd": 1}),
+    "hw_generic": (0, {"fused_hw_special": 0}),
     "c16_ws3": (0, {"tile_kind": 2, "fused_cluster": 16, "fused_wsmem": 3, "fused_stash_kb": 0}),
     "c16_ws3_st12": (0, {"tile_kind": 2, "fused_cluster": 16, "fused_wsmem": 3, "fused_stash_kb": 12}),
     "c16_ws0": (0, {"tile_kind": 2, "fused_cluster": 16, "fused_wsmem": 0}),
@@ -319,7 +320,7 @@ def main():
 
             for name in args.variants.split(","):
                 flags, tun = VARIANTS[name]
-                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": -1, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, "tile_switch": 1, "tile_rpol": 0, "tile_max_slots": 0, "tile_split_copies": 1, "tile_draw": 4, "tile_chunk_kb_fwd": 56, "tile_min_mb_light": 190, "tile_wgrad": 1, "fused_wsmem": -1, "tile_light_fwd": 0, **tun}.items():
+                for k, v in {"l2_chunk_mb": 100000, "fused_kind": 0, "fused_cluster": 0, "fused_threads": 0, "fused_prefetch": 0, "fused_occ": 4, "fused_weight_ratio_x100": 100, "fused_group_kb": 128, "gemm_big_tiles": 0, "fused_stash_kb": -1, "gemm_tf32x3": 1, "gemm_umma": 1, "tile_kind": 0, "tile_lag": 0, "tile_ksplit_tiles": 0, "tile_m": 0, "tile_gemm_ctas": 0, "tile_chunk_kb": 28, "tile_nodeps": 0, "tile_switch": 1, "tile_rpol": 0, "tile_max_slots": 0, "tile_split_copies": 1, "tile_draw": 4, "tile_chunk_kb_fwd": 56, "tile_min_mb_light": 190, "tile_wgrad": 1, "fused_wsmem": -1, "tile_light_fwd": 0, "fused_hw_special": 1, **tun}.items():
                     L.check(lib.gml_set_tunable(k.encode(), v))
                 # workspace sizes depend on the tile tunables: re-query for this variant
                 b.ws_bytes = lib.gml_mmtm_bwd_workspace_bytes(b.dims)
