@@ -99,6 +99,8 @@ int gml_profile_read(int tag, double* total_ms, int64_t* launches);
  *   "fused_occ", "fused_stash_kb", "fused_group_kb", "fused_weight_ratio_x100"
  *                    occupancy / stash / group size / path-selection threshold ("fused_prefetch" is accepted and ignored)
  *   "fused_wsmem"    -1 auto | bit 0 / bit 1: first / second FC's weight slice of a CTA lives in shared memory
+ *   "fused_stash_kb" -1 auto (24 KB; none for a backward whose weight slices are in shared memory) | KB per CTA
+ *   "fused_hw_special" 1 plane-size-specialised cluster kernels for 28 x 28 planes | 0 generic instantiation
  *   "gemm_umma"      1 tcgen05 (TMEM) 3xTF32 kernel for FC problems above ~1e8 MACs | 0 never
  *   "gemm_tf32x3"    1 mma.sync 3xTF32 for large problems the tcgen05 kernel does not take | 0 CUDA cores
  *   "gemm_big_tiles" 1 opt-in 128x128 CUDA-core tiles
